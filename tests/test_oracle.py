@@ -173,7 +173,7 @@ def test_binning_oracle(dim, mode, tb):
     perm = co.stable_sort(keys)
     assert (perm == np.argsort(keys, kind="stable").astype(np.uint32)).all()
     # particles outside the grid are counted
-    x[0, 0] = 0.001
+    x[0, 0] = -0.02  # (Q4: truncation keeps x in (-0.5dx, 0.5dx) at base 0)
     x[1, 1] = 0.999
     assert co.cell_keys(x, res, mode, tb)[2] == 2
 
