@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the advance() hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One "step" = one advance() (P2G + grid update + G2P, plus the per-step re-binning) over the whole
+synthetic scene.  `value` is device-timed with inputs resident in HBM; `e2e` goes through the C-ABI with
+HOST buffers: every step uploads the particle state from pinned host memory, advances once and downloads
+the new state (the reference's per-step snapshot pattern, src/solver.cpp:50-59).
+
+Workloads (BASELINE.json configs; scenes from BASELINE.md §4):
+  cfg4      3D snow, cube<3>(256,0.25,0.5) = 16 777 216 particles, 512^3 grid   [default, all N; strong scaling]
+  snow128   3D snow, cube<3>(154,0.2,0.8)  =  3 652 264 particles, 128^3 grid   (the 1e9 single-GPU target scene)
+  cfg2      3D jelly, cube<3>(64,0.375,0.625) = 262 144 particles, 128^3 grid
+  cfg3      3D liquid, 126^3 block = 2 000 376 particles, 256^3 grid
+  cfg1      2D snow, two 50x50 squares = 5 000 particles, 64^2 grid (README scene)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SNOW, JELLY, LIQUID = 0, 1, 2
+
+
+def scene(name: str):
+    """-> (positions (n,dim) float32, model, res, description)"""
+    import nuclearmpm_b200 as nm
+    if name == "cfg4":
+        return nm.cube(3, 256, 0.25, 0.5), SNOW, 512, "cfg4: 3D snow cube<3>(256,0.25,0.5) 16777216 p, 512^3 grid"
+    if name == "snow128":
+        return nm.cube(3, 154, 0.2, 0.8), SNOW, 128, "3D snow cube<3>(154,0.2,0.8) 3652264 p, 128^3 grid"
+    if name == "cfg2":
+        return nm.cube(3, 64, 0.375, 0.625), JELLY, 128, "cfg2: 3D jelly cube<3>(64,0.375,0.625) 262144 p, 128^3 grid"
+    if name == "cfg3":
+        return (nm.cube(3, 126, 0.05, 0.05 + 62.5 / 256), LIQUID, 256,
+                "cfg3: 3D liquid 126^3 block 2000376 p, 256^3 grid")
+    if name == "cfg1":
+        a = nm.cube(2, 50, 0.4, 0.6)
+        b = a - np.array([0, 0.35], np.float32)
+        return np.concatenate([a, b]).astype(np.float32), SNOW, 64, "cfg1: 2D snow two 50x50 squares 5000 p, 64^2 grid"
+    raise SystemExit(f"unknown workload {name}")
+
+
+# algorithmic bytes per particle-step: P2G reads S+2 floats, G2P reads x,F,Jp and writes S
+ALGO_BYTES = {3: dict(p2g=108, g2p=152), 2: dict(p2g=60, g2p=80)}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.lines = device, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline: the reference's own advance() (oracle/_ref, -Ofast build) or the oracle port
+# ----------------------------------------------------------------------------------------------
+def cpu_sample(workload: str, budget_s: float):
+    """A bounded sample of `workload` for the CPU: same material, spacing, dt and grid; fewer particles."""
+    import nuclearmpm_b200 as nm
+    x, model, res, desc = scene(workload)
+    dim = x.shape[1]
+    if workload == "cfg4":
+        m = 128 if budget_s >= 8 else 64
+        xs = nm.cube(3, m, 0.25, 0.25 + (m - 1) * (0.25 / 255))
+        what = f"cube<3>({m}) sub-block of cfg4 ({len(xs)} p, same spacing, 512^3 grid)"
+    elif workload == "snow128":
+        m = 64
+        xs = nm.cube(3, m, 0.2, 0.2 + (m - 1) * (0.6 / 153))
+        what = f"cube<3>({m}) sub-block of the scene ({len(xs)} p, same spacing, 128^3 grid)"
+    elif workload == "cfg3":
+        m = 64
+        xs = nm.cube(3, m, 0.05, 0.05 + (m - 1) * (62.5 / 256 / 125))
+        what = f"{m}^3 sub-block ({len(xs)} p, same spacing, 256^3 grid)"
+    else:
+        xs, what = x, "the full scene"
+    return xs, model, res, dim, what
+
+
+def cpu_reference_rate(workload: str, steps: int, warmup: int, budget_s: float = 20.0):
+    from oracle import cpu_oracle as co
+    kind = "ref_fast" if co.available("ref_fast") else "port"
+    xs, model, res, dim, what = cpu_sample(workload, budget_s)
+    sim = co.CpuSim(xs, model, res, kind=kind)
+    if warmup:
+        sim.time_advance(warmup)
+    t = sim.time_advance(steps)
+    rate = len(xs) * steps / t
+    return dict(value=rate, unit="particle-steps/s", cores=1, kind="reference" if kind == "ref_fast" else "port",
+                sample=f"{what}; {steps} advance() steps in {t:.2f} s on 1 host core "
+                       f"({'reference nclr.h, -Ofast, Eigen stand-in' if kind == 'ref_fast' else 'oracle port, -O2'})"), t
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    x, model, res, desc = scene(args.workload)
+    per_step_budget = max(1.0, 150.0 / max(1, args.steps + args.warmup))
+    cb, t = cpu_reference_rate(args.workload, args.steps, args.warmup, budget_s=per_step_budget)
+    line = {
+        "impl": "reference", "metric": "particle-steps/s", "value": cb["value"], "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "particles": int(len(x)), "grid_res": res, "dim": int(x.shape[1]),
+                   "material": ["snow", "jelly", "liquid"][model]},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import nuclearmpm_b200 as nm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    x, model, res, desc = scene(args.workload)
+    dim = x.shape[1]
+    n_total = len(x)
+
+    if world > 1:
+        from nuclearmpm_b200 import slab
+        result = slab.bench_slabs(args, x, model, res, desc, rank, world, local)
+        if rank == 0:
+            print(json.dumps(result))
+        dist.destroy_process_group()
+        return
+
+    stream = torch.cuda.Stream()
+    sim = nm.MPMSimulation(x, model, res, device=local, sort_every=args.sort_every, p2g_variant=args.p2g_variant)
+    sim.set_stream(stream.cuda_stream)
+
+    def sync():
+        sim.synchronize()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------------
+    sim.advance(args.warmup)
+    sync()
+    l0 = sim.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        sync()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            sim.advance(args.steps)
+            e1.record(stream)
+        sync()
+        ms = e0.elapsed_time(e1)
+    launches = sim.launch_count() - l0
+    clocks = clk.summary()
+    value = n_total * args.steps / (ms * 1e-3)
+
+    # ---- per-phase timing (separate pass; events per phase serialise the step) ----------------
+    sim.timing_enable(True)
+    sim.timing_read(reset=True)
+    prof_steps = min(args.steps, 20)
+    sim.advance(prof_steps)
+    sync()
+    tm = sim.timing_read(reset=True)
+    sim.timing_enable(False)
+    peak, peak_src = measured_peak_gbs()
+    ab = ALGO_BYTES[dim]
+    phases = {}
+    for k in ("sort", "p2g", "grid", "g2p"):
+        phases[k + "_ms"] = tm[k] / max(1, tm["steps"])
+    dom = "g2p" if phases["g2p_ms"] >= phases["p2g_ms"] else "p2g"
+    dom_ms = phases[dom + "_ms"]
+    achieved = ab[dom] * n_total / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_particle": ab[dom],
+                "other": {k: {"ms": phases[k + "_ms"],
+                              "achieved_GBps": ab[k] * n_total / (phases[k + "_ms"] * 1e-3) / 1e9 if phases[k + "_ms"] > 0 else 0.0}
+                          for k in ("p2g", "g2p")},
+                "phase_ms": phases}
+
+    # ---- end to end through the C-ABI with host buffers ---------------------------------------
+    st = sim.particles()
+    host = {k: torch.from_numpy(v).pin_memory() for k, v in st.items()}
+    hnp = {k: v.numpy() for k, v in host.items()}
+    e2e_steps = max(3, min(args.steps, 10))
+    L = sim._L
+    import ctypes as C
+    fp = C.POINTER(C.c_float)
+    ptr = {k: hnp[k].ctypes.data_as(fp) for k in hnp}
+
+    def e2e_step():
+        rc = L.nmpm_upload_particles(sim._h, ptr["x"], ptr["v"], ptr["F"], ptr["C"], ptr["Jp"])
+        rc |= L.nmpm_advance(sim._h, 1)
+        rc |= L.nmpm_download_particles(sim._h, ptr["x"], ptr["v"], ptr["F"], ptr["C"], ptr["Jp"])
+        if rc:
+            raise RuntimeError(L.nmpm_last_error(sim._h).decode())
+
+    e2e_step()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    sync()
+    t_e2e = time.perf_counter() - t0
+    state_bytes = sum(v.nbytes for v in hnp.values())
+    e2e = {"value": n_total * e2e_steps / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": state_bytes,
+           "d2h_bytes_per_step": state_bytes, "steps": e2e_steps,
+           "what": "per step: nmpm_upload_particles (pinned host -> device) + nmpm_advance(1) + "
+                   "nmpm_download_particles (device -> pinned host, input order)"}
+
+    # ---- CPU baseline (rank 0, bounded sample) -------------------------------------------------
+    if args.no_cpu:
+        cpu = None
+    else:
+        cpu, _ = cpu_reference_rate(args.workload, 2 if n_total > 1_000_000 else 10, 0, budget_s=10.0)
+
+    line = {
+        "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "particles": int(n_total), "grid_res": res, "dim": dim,
+                   "material": ["snow", "jelly", "liquid"][model], "sort_every": args.sort_every,
+                   "l2_policy": "inputs larger than L2 (particle store + grid >> 126 MB)" if n_total * 116 > 2e8
+                   else "working set smaller than L2 (scene is small); no flush"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="cfg4")
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--sort-every", type=int, default=1)
+    ap.add_argument("--p2g-variant", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,153 @@
+/* nmpm.h — C-ABI of the B200-native MLS-MPM step ("libnmpm.so").
+ *
+ * This is the drop-in boundary for the reference's per-step hot path.  The reference has no FFI
+ * table: its boundary is the C++ class surface of src/nclr.h (MPMSimulation<dim>, src/nclr.h:63-87)
+ * consumed at src/example.cpp:46,53,65,77 and src/solver.cpp:46-59,100-104,184-188.  Each entry
+ * point below names the reference interface it replaces; include/nclr.h (same namespace, types and
+ * signatures as the reference header) is the binding a maintainer uses — see INTEGRATION.md.
+ *
+ * Plain pointers and sizes only.  All `const float*` particle inputs are HOST pointers in the
+ * interchange layout:  x,v : n*dim ;  F,C : n*dim*dim, per particle column-major (Eigen storage,
+ * M(i,j) at [i + j*dim]) ;  Jp,mass,volume : n.  A NULL input means the reference's default
+ * (src/nclr.h:46-47: v=0, F=diag<dim>(1) [Q1: diag(1,1,0) in 3D], C=0, Jp=1, mass=volume=1).
+ * Grid outputs: node index x*n1+y (2D) / (x*n1+y)*n1+z (3D), n1=res+1 (src/nclr.h:141-142,152).
+ *
+ * There is no CPU fallback: every compute entry point fails with NMPM_ERR_NO_DEVICE / NMPM_ERR_CUDA
+ * when no sm_100 device is usable.
+ */
+#ifndef NMPM_H
+#define NMPM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMPM_VERSION 100
+
+typedef struct nmpm_sim *nmpm_handle;
+
+enum nmpm_status {
+    NMPM_OK = 0,
+    NMPM_ERR_INVALID = 1,     /* bad argument */
+    NMPM_ERR_CUDA = 2,        /* CUDA runtime error; see nmpm_last_error */
+    NMPM_ERR_OUT_OF_GRID = 3, /* a particle's 3-wide stencil left [0,res]: the reference throws
+                                 std::out_of_range from .at() (src/nclr.h:113,163,199; Q5) */
+    NMPM_ERR_NO_DEVICE = 4
+};
+
+/* enum class MaterialModel — src/nclr.h:57-61 */
+enum nmpm_model { NMPM_SNOW = 0, NMPM_JELLY = 1, NMPM_LIQUID = 2 };
+
+/* phases of advance() — src/nclr.h:80-84 */
+enum nmpm_phase { NMPM_PHASE_P2G = 0, NMPM_PHASE_GRID_OP = 1, NMPM_PHASE_G2P = 2 };
+
+/* tunables that do not change results beyond float summation order */
+typedef struct nmpm_options {
+    int device;       /* CUDA device ordinal (default 0) */
+    int sort_every;   /* re-bin + radix-sort particles by cell key every k steps (default 1; 0 = never) */
+    int p2g_variant;  /* 0 = auto, 1 = per-particle float4 REDs, 2 = cell-segmented register accumulation */
+    int use_graph;    /* capture the step into a CUDA graph and replay it (default 1) */
+    int slab_x0;      /* multi-GPU x-slab: first owned node plane (default 0) */
+    int slab_x1;      /* multi-GPU x-slab: one past the last owned node plane (default res+1) */
+    int reserved[10];
+} nmpm_options;
+
+void nmpm_default_options(nmpm_options *opt);
+
+/* MPMSimulation<dim>::MPMSimulation(particles, model, res, dt, E, nu, gravity) — src/nclr.h:74-78.
+ * SoA host arrays in the interchange layout. */
+int nmpm_create(int dim, int model, int res, float dt, float E, float nu, float gravity, size_t n,
+                const float *x, const float *v, const float *F, const float *C, const float *Jp,
+                const float *mass, const float *volume, const nmpm_options *opt, nmpm_handle *out);
+
+/* Same constructor, taking the reference's AoS std::vector<Particle<dim>>::data() directly
+ * (struct Particle — src/nclr.h:20-48: x, v, F, C, Jp, mass, volume, c; 64 B in 2D, 112 B in 3D).
+ * `stride` = sizeof(Particle<dim>).  The int colour `c` is kept and returned by download_aos. */
+int nmpm_create_aos(int dim, int model, int res, float dt, float E, float nu, float gravity, size_t n,
+                    const void *particles_aos, size_t stride, const nmpm_options *opt, nmpm_handle *out);
+
+void nmpm_destroy(nmpm_handle h);
+
+/* MPMSimulation::advance() × nsteps — src/nclr.h:80-84.  Asynchronous on the sim's stream unless an
+ * error must be reported; NMPM_ERR_OUT_OF_GRID is reported by the call that detects it or by the
+ * next synchronising call (nmpm_synchronize / any download). */
+int nmpm_advance(nmpm_handle h, int nsteps);
+
+/* One phase of advance() (p2g / grid_op / g2p are private in the reference — src/nclr.h:104,167,263):
+ * test and profiling hook; the post-P2G grid is needed for conservation checks (Q6). */
+int nmpm_phase(nmpm_handle h, int phase);
+
+int nmpm_synchronize(nmpm_handle h);
+
+/* MPMSimulation::particles() — src/nclr.h:86.  Input order, forever.  Any output may be NULL. */
+int nmpm_download_particles(nmpm_handle h, float *x, float *v, float *F, float *C, float *Jp);
+int nmpm_download_particles_aos(nmpm_handle h, void *particles_aos, size_t stride);
+/* positions only (src/example.cpp:77 consumes just x and c every 10th step) */
+int nmpm_download_positions(nmpm_handle h, float *x);
+
+/* MPMSimulation::grid() — src/nclr.h:87.  (res+1)^dim cells in reference index order.
+ * Returns NMPM_OK and *cells_out = 0 before the first p2g (the reference's grid() is empty then,
+ * src/solver.cpp:52-57).  gv: cells*dim (momentum after P2G, velocity after grid_op), gm: cells. */
+int nmpm_download_grid(nmpm_handle h, float *gv, float *gm, size_t *cells_out);
+/* struct Cell<dim> AoS — src/nclr.h:50-55 (12 B in 2D, 16 B in 3D) */
+int nmpm_download_grid_aos(nmpm_handle h, void *cells_aos, size_t stride, size_t *cells_out);
+
+/* Replace the particle state (teacher-forced parity tests / resume from a snapshot: the reference
+ * does this by constructing a new sim from a saved particle vector).  n must match. */
+int nmpm_upload_particles(nmpm_handle h, const float *x, const float *v, const float *F, const float *C,
+                          const float *Jp);
+
+size_t nmpm_num_particles(nmpm_handle h);
+size_t nmpm_grid_cells(nmpm_handle h); /* (res+1)^dim */
+/* public consts mu_0 / lambda_0 — src/nclr.h:71-72 (computed in fp32 exactly like the ctor) */
+int nmpm_lame(nmpm_handle h, float *mu_0, float *lambda_0);
+
+/* Binning debug hook (K0): recompute cell keys from the current positions and radix-sort them.
+ * base: n*dim int32 in CURRENT device order; keys_sorted: n; perm: n (device slot of the i-th sorted
+ * particle); ids: n original (input-order) index of each device slot.  Any output may be NULL. */
+int nmpm_sort_debug(nmpm_handle h, int32_t *base, uint32_t *keys_unsorted, uint32_t *keys_sorted,
+                    uint32_t *perm, uint32_t *ids);
+/* key layout used by the solver: tile bits per axis (blocked key mode 1 of oracle/nclr_oracle.h) */
+int nmpm_key_tile_bits(nmpm_handle h);
+
+/* Device-side SVD / polar / stress unit hooks (nclr_svd, nclr_polar — src/nclr_math.h:50-98;
+ * first_piola_kirchoff_stress — src/nclr.h:313-337).  count matrices, host pointers, column-major. */
+int nmpm_svd_batch(int dim, size_t count, const float *A, float *U, float *sig, float *V, int device);
+int nmpm_polar_batch(int dim, size_t count, const float *A, float *R, int device);
+int nmpm_affine_debug(nmpm_handle h, float *A_out /* n*dim*dim, input order */);
+
+/* Timing: accumulated CUDA-event milliseconds per phase since the last reset (only recorded when
+ * enabled; recording breaks graph replay into per-kernel launches). */
+enum nmpm_timer { NMPM_T_SORT = 0, NMPM_T_P2G = 1, NMPM_T_GRID = 2, NMPM_T_G2P = 3, NMPM_T_CLEAR = 4, NMPM_T_COUNT = 8 };
+int nmpm_timing_enable(nmpm_handle h, int on);
+int nmpm_timing_read(nmpm_handle h, float *ms /* NMPM_T_COUNT */, int *steps, int reset);
+/* number of kernel launches issued by the library for this sim since creation */
+long long nmpm_launch_count(nmpm_handle h);
+
+/* Stream plumbing: run on an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream). */
+int nmpm_set_stream(nmpm_handle h, void *cuda_stream);
+void *nmpm_get_stream(nmpm_handle h);
+
+/* Multi-GPU slab plumbing (one process per GPU; the exchange itself is done by the caller with
+ * NCCL send/recv on these device buffers, on the sim's stream — SURVEY.md §8(e)). */
+/* device pointer to node plane `x_plane` of the grid (contiguous n1^(dim-1) float4 nodes) */
+void *nmpm_grid_plane_ptr(nmpm_handle h, int x_plane);
+size_t nmpm_grid_plane_bytes(nmpm_handle h);
+/* add `planes` received node planes (device buffer) into the grid starting at x_plane */
+int nmpm_grid_add_planes(nmpm_handle h, int x_plane, int planes, const void *device_src);
+/* After G2P: move particles whose base.x left [slab_x0, slab_x1) into the send buffers.
+ * Returns counts; payload = 28 floats per particle (27 state + id bits). */
+int nmpm_migrate_pack(nmpm_handle h, void **send_left, size_t *n_left, void **send_right, size_t *n_right);
+int nmpm_migrate_unpack(nmpm_handle h, const void *recv_device, size_t n_recv);
+size_t nmpm_migrate_record_bytes(nmpm_handle h);
+
+const char *nmpm_last_error(nmpm_handle h); /* h may be NULL: last creation error */
+const char *nmpm_build_info(void);          /* arch, compiler, date */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMPM_H */

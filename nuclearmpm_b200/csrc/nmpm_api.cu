@@ -1,0 +1,822 @@
+// C-ABI implementation (include/nmpm.h): owns the device particle store, the grid, the stream and
+// the per-step launch sequence.  No CPU fallback: without a usable CUDA device every compute entry
+// point returns NMPM_ERR_NO_DEVICE / NMPM_ERR_CUDA.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/nmpm.h"
+#include "nmpm_kernels.cuh"
+#include "nmpm_p2g_cell.cuh"
+#include "nmpm_sort.cuh"
+
+using namespace nmpm;
+
+#define NMPM_STR2(x) #x
+#define NMPM_STR(x) NMPM_STR2(x)
+
+namespace {
+thread_local std::string g_create_error;
+
+__global__ void __launch_bounds__(256) k_add_planes(float4* __restrict__ dst, const float4* __restrict__ src, size_t count) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float4 a = dst[i];
+    const float4 b = src[i];
+    a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+    dst[i] = a;
+}
+}  // namespace
+
+struct nmpm_sim {
+    int dim = 0, model = 0, res = 0;
+    size_t n = 0, cells = 0;
+    MaterialParams P{};
+    nmpm_options opt{};
+    float E = 0, nu = 0, gravity = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    ParticleStore store[2]{};
+    int cur = 0;
+    float4* grid = nullptr;
+    bool grid_valid = false;  // false until the first p2g: the reference's grid() is empty (src/solver.cpp:52-57)
+
+    SortWorkspace sort;
+    int tiles_per_axis = 0, key_bits = 0;
+
+    int* d_error = nullptr;
+    int* h_error = nullptr;  // pinned
+    bool error_latched = false;
+
+    float* staging = nullptr;  // device scratch for import/export
+    size_t staging_bytes = 0;
+
+    long long steps_done = 0;
+    long long launches = 0;
+    int phase_next = 0;
+
+    bool timing = false;
+    cudaEvent_t ev[6]{};
+    float t_ms[NMPM_T_COUNT]{};
+    int t_steps = 0;
+
+    std::string last_error;
+};
+
+#define CUDA_TRY(h, expr)                                                                              \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            char _buf[512];                                                                            \
+            snprintf(_buf, sizeof(_buf), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                     __LINE__);                                                                        \
+            if (h) (h)->last_error = _buf;                                                             \
+            else                                                                                       \
+                g_create_error = _buf;                                                                 \
+            return NMPM_ERR_CUDA;                                                                      \
+        }                                                                                              \
+    } while (0)
+
+#define NMPM_DISPATCH_DIM(h, CALL)  \
+    do {                            \
+        if ((h)->dim == 2) {        \
+            constexpr int D = 2;    \
+            CALL;                   \
+        } else {                    \
+            constexpr int D = 3;    \
+            CALL;                   \
+        }                           \
+    } while (0)
+
+#define NMPM_DISPATCH(h, CALL)                  \
+    do {                                        \
+        if ((h)->dim == 2) {                    \
+            constexpr int D = 2;                \
+            if ((h)->model == 0) {              \
+                constexpr int MODEL = 0;        \
+                CALL;                           \
+            } else if ((h)->model == 1) {       \
+                constexpr int MODEL = 1;        \
+                CALL;                           \
+            } else {                            \
+                constexpr int MODEL = 2;        \
+                CALL;                           \
+            }                                   \
+        } else {                                \
+            constexpr int D = 3;                \
+            if ((h)->model == 0) {              \
+                constexpr int MODEL = 0;        \
+                CALL;                           \
+            } else if ((h)->model == 1) {       \
+                constexpr int MODEL = 1;        \
+                CALL;                           \
+            } else {                            \
+                constexpr int MODEL = 2;        \
+                CALL;                           \
+            }                                   \
+        }                                       \
+    } while (0)
+
+static inline unsigned blocks_for(size_t n, int threads) { return (unsigned) ((n + threads - 1) / threads); }
+
+static int ensure_staging(nmpm_sim* h, size_t bytes) {
+    if (h->staging_bytes >= bytes) return NMPM_OK;
+    if (h->staging) CUDA_TRY(h, cudaFree(h->staging));
+    h->staging = nullptr;
+    h->staging_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->staging, bytes));
+    h->staging_bytes = bytes;
+    return NMPM_OK;
+}
+
+static int alloc_store(nmpm_sim* h, ParticleStore& S) {
+    const size_t n = h->n ? h->n : 1;
+    const int nq = (h->dim == 3) ? 6 : 3;
+    for (int k = 0; k < nq; ++k) CUDA_TRY(h, cudaMalloc(&S.q[k], n * sizeof(float4)));
+    CUDA_TRY(h, cudaMalloc(&S.s, n * sizeof(float)));
+    CUDA_TRY(h, cudaMalloc(&S.mv, n * sizeof(float2)));
+    CUDA_TRY(h, cudaMalloc(&S.id, n * sizeof(uint32_t)));
+    return NMPM_OK;
+}
+
+static void free_store(ParticleStore& S) {
+    for (int k = 0; k < 6; ++k)
+        if (S.q[k]) cudaFree(S.q[k]);
+    if (S.s) cudaFree(S.s);
+    if (S.mv) cudaFree(S.mv);
+    if (S.id) cudaFree(S.id);
+    S = ParticleStore{};
+}
+
+// constants exactly as the reference ctor computes them (src/nclr.h:74-78, :285, :325)
+static void fill_params(nmpm_sim* h, float dt, float E, float nu, float gravity) {
+    MaterialParams& P = h->P;
+    P.res = h->res;
+    P.n1 = h->res + 1;
+    P.dt = dt;
+    P.dx = (float) (1.0 / h->res);
+    P.inv_dx = 1 / P.dx;
+    P.mu_0 = E / (2 * (1 + nu));
+    P.lambda_0 = E * nu / ((1 + nu) * (1 - 2 * nu));
+    P.Dinv = 4 * P.inv_dx * P.inv_dx;
+    P.vmax = (float) ((double) P.dx * 0.9 / (double) dt);
+    P.dt_gravity = dt * gravity;
+}
+
+static int create_common(int dim, int model, int res, float dt, float E, float nu, float gravity, size_t n,
+                         const nmpm_options* opt, nmpm_sim** out) {
+    if (!out) return NMPM_ERR_INVALID;
+    *out = nullptr;
+    if ((dim != 2 && dim != 3) || model < 0 || model > 2 || res < 4 || n > 0xFFFFFFF0ull) {
+        g_create_error = "invalid argument (dim must be 2 or 3, model 0..2, res >= 4)";
+        return NMPM_ERR_INVALID;
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        g_create_error = "no CUDA device: libnmpm has no CPU fallback";
+        return NMPM_ERR_NO_DEVICE;
+    }
+    nmpm_sim* h = new (std::nothrow) nmpm_sim();
+    if (!h) return NMPM_ERR_INVALID;
+    nmpm_default_options(&h->opt);
+    if (opt) h->opt = *opt;
+    if (h->opt.device < 0 || h->opt.device >= count) {
+        g_create_error = "invalid device ordinal";
+        delete h;
+        return NMPM_ERR_INVALID;
+    }
+    h->dim = dim, h->model = model, h->res = res, h->n = n;
+    h->E = E, h->nu = nu, h->gravity = gravity;
+    h->device = h->opt.device;
+    fill_params(h, dt, E, nu, gravity);
+    if (h->opt.slab_x1 <= 0) h->opt.slab_x1 = res + 1;
+    const size_t n1 = (size_t) res + 1;
+    h->cells = (dim == 3) ? n1 * n1 * n1 : n1 * n1;
+    h->tiles_per_axis = (int) ((n1 + (1 << kTileBits) - 1) >> kTileBits);
+    {
+        size_t tiles = 1;
+        for (int d = 0; d < dim; ++d) tiles *= (size_t) h->tiles_per_axis;
+        int bits = 0;
+        while ((1ull << bits) < tiles) ++bits;
+        h->key_bits = bits + dim * kTileBits;
+        if (h->key_bits > 32) {
+            g_create_error = "grid too large for 32-bit cell keys";
+            delete h;
+            return NMPM_ERR_INVALID;
+        }
+    }
+    *out = h;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+    if (int rc = alloc_store(h, h->store[0])) return rc;
+    if (int rc = alloc_store(h, h->store[1])) return rc;
+    CUDA_TRY(h, cudaMalloc(&h->grid, h->cells * sizeof(float4)));
+    CUDA_TRY(h, cudaMalloc(&h->d_error, sizeof(int)));
+    CUDA_TRY(h, cudaMemset(h->d_error, 0, sizeof(int)));
+    CUDA_TRY(h, cudaMallocHost(&h->h_error, sizeof(int)));
+    *h->h_error = 0;
+    // sort workspace
+    const size_t nn = n ? n : 1;
+    h->sort.ntiles = (uint32_t) ((nn + kSortTile - 1) / kSortTile);
+    CUDA_TRY(h, cudaMalloc(&h->sort.keys_a, nn * sizeof(uint32_t)));
+    CUDA_TRY(h, cudaMalloc(&h->sort.keys_b, nn * sizeof(uint32_t)));
+    CUDA_TRY(h, cudaMalloc(&h->sort.vals_a, nn * sizeof(uint32_t)));
+    CUDA_TRY(h, cudaMalloc(&h->sort.vals_b, nn * sizeof(uint32_t)));
+    CUDA_TRY(h, cudaMalloc(&h->sort.hist, (size_t) kRadix * h->sort.ntiles * sizeof(uint32_t)));
+    CUDA_TRY(h, cudaMalloc(&h->sort.digit_total, kRadix * sizeof(uint32_t)));
+    CUDA_TRY(h, cudaMalloc(&h->sort.digit_base, kRadix * sizeof(uint32_t)));
+    CUDA_TRY(h, cudaMalloc(&h->sort.done_counter, sizeof(unsigned int)));
+    CUDA_TRY(h, cudaMemset(h->sort.done_counter, 0, sizeof(unsigned int)));
+    for (auto& e : h->ev) CUDA_TRY(h, cudaEventCreate(&e));
+    return NMPM_OK;
+}
+
+extern "C" {
+
+void nmpm_default_options(nmpm_options* opt) {
+    if (!opt) return;
+    std::memset(opt, 0, sizeof(*opt));
+    opt->device = 0;
+    opt->sort_every = 1;
+    opt->p2g_variant = 0;
+    opt->use_graph = 1;
+    opt->slab_x0 = 0;
+    opt->slab_x1 = 0;  // 0 = res+1
+}
+
+const char* nmpm_build_info(void) {
+    return "libnmpm " __DATE__ " " __TIME__ " sm_100a nvcc " NMPM_STR(__CUDACC_VER_MAJOR__) "." NMPM_STR(__CUDACC_VER_MINOR__);
+}
+
+const char* nmpm_last_error(nmpm_handle h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+
+void nmpm_destroy(nmpm_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_store(h->store[0]);
+    free_store(h->store[1]);
+    if (h->grid) cudaFree(h->grid);
+    if (h->d_error) cudaFree(h->d_error);
+    if (h->h_error) cudaFreeHost(h->h_error);
+    if (h->staging) cudaFree(h->staging);
+    cudaFree(h->sort.keys_a);
+    cudaFree(h->sort.keys_b);
+    cudaFree(h->sort.vals_a);
+    cudaFree(h->sort.vals_b);
+    cudaFree(h->sort.hist);
+    cudaFree(h->sort.digit_total);
+    cudaFree(h->sort.digit_base);
+    cudaFree(h->sort.done_counter);
+    for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+}
+
+int nmpm_create(int dim, int model, int res, float dt, float E, float nu, float gravity, size_t n, const float* x,
+                const float* v, const float* F, const float* C, const float* Jp, const float* mass,
+                const float* volume, const nmpm_options* opt, nmpm_handle* out) {
+    nmpm_sim* h = nullptr;
+    int rc = create_common(dim, model, res, dt, E, nu, gravity, n, opt, &h);
+    if (rc != NMPM_OK) {
+        if (h) {
+            g_create_error = h->last_error;
+            nmpm_destroy(h);
+            if (out) *out = nullptr;
+        }
+        return rc;
+    }
+    if (n && !x) {
+        g_create_error = "x must not be NULL";
+        nmpm_destroy(h);
+        *out = nullptr;
+        return NMPM_ERR_INVALID;
+    }
+    if (n) {
+        // stage the interchange arrays on the device, then pack into the SoA store (K5)
+        const size_t D = (size_t) dim;
+        const size_t words = n * (2 * D + 2 * D * D + 3);
+        rc = ensure_staging(h, words * sizeof(float));
+        if (rc == NMPM_OK) {
+            float* p = h->staging;
+            auto up = [&](const float* src, size_t cnt) -> float* {
+                if (!src) return nullptr;
+                float* dst = p;
+                p += cnt;
+                if (cudaMemcpyAsync(dst, src, cnt * sizeof(float), cudaMemcpyHostToDevice, h->stream) != cudaSuccess)
+                    rc = NMPM_ERR_CUDA;
+                return dst;
+            };
+            float* dx = up(x, n * D);
+            float* dv = up(v, n * D);
+            float* dF = up(F, n * D * D);
+            float* dC = up(C, n * D * D);
+            float* dJ = up(Jp, n);
+            float* dm = up(mass, n);
+            float* dvol = up(volume, n);
+            if (rc == NMPM_OK) {
+                NMPM_DISPATCH_DIM(h, (k_import_soa<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(
+                                         dx, dv, dF, dC, dJ, dm, dvol, (uint32_t) n, h->store[0], 0)));
+                h->launches++;
+                if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+                    rc = NMPM_ERR_CUDA;
+            }
+        }
+        if (rc != NMPM_OK) {
+            g_create_error = h->last_error.empty() ? std::string("particle upload failed: ") +
+                                                         cudaGetErrorString(cudaGetLastError())
+                                                   : h->last_error;
+            nmpm_destroy(h);
+            *out = nullptr;
+            return rc;
+        }
+    }
+    *out = h;
+    return NMPM_OK;
+}
+
+int nmpm_create_aos(int dim, int model, int res, float dt, float E, float nu, float gravity, size_t n,
+                    const void* particles_aos, size_t stride, const nmpm_options* opt, nmpm_handle* out) {
+    const size_t rec = (dim == 3) ? 112 : 64;
+    if ((dim == 2 || dim == 3) && (stride < rec || stride % 4 != 0 || (n && !particles_aos))) {
+        g_create_error = "AoS stride must be >= sizeof(Particle<dim>) (64 B in 2D, 112 B in 3D) and a multiple of 4";
+        if (out) *out = nullptr;
+        return NMPM_ERR_INVALID;
+    }
+    nmpm_sim* h = nullptr;
+    int rc = create_common(dim, model, res, dt, E, nu, gravity, n, opt, &h);
+    if (rc == NMPM_OK && n) {
+        rc = ensure_staging(h, n * stride);
+        if (rc == NMPM_OK) {
+            cudaError_t e = cudaMemcpyAsync(h->staging, particles_aos, n * stride, cudaMemcpyHostToDevice, h->stream);
+            if (e == cudaSuccess) {
+                NMPM_DISPATCH_DIM(h, (k_import_aos<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(
+                                         h->staging, stride / 4, (uint32_t) n, h->store[0])));
+                h->launches++;
+                e = cudaStreamSynchronize(h->stream);
+            }
+            if (e != cudaSuccess) {
+                h->last_error = std::string("AoS upload failed: ") + cudaGetErrorString(e);
+                rc = NMPM_ERR_CUDA;
+            }
+        }
+    }
+    if (rc != NMPM_OK) {
+        if (h) {
+            g_create_error = h->last_error;
+            nmpm_destroy(h);
+        }
+        if (out) *out = nullptr;
+        return rc;
+    }
+    *out = h;
+    return NMPM_OK;
+}
+
+size_t nmpm_num_particles(nmpm_handle h) { return h ? h->n : 0; }
+size_t nmpm_grid_cells(nmpm_handle h) { return h ? h->cells : 0; }
+int nmpm_key_tile_bits(nmpm_handle) { return kTileBits; }
+long long nmpm_launch_count(nmpm_handle h) { return h ? h->launches : 0; }
+
+int nmpm_lame(nmpm_handle h, float* mu_0, float* lambda_0) {
+    if (!h) return NMPM_ERR_INVALID;
+    if (mu_0) *mu_0 = h->P.mu_0;
+    if (lambda_0) *lambda_0 = h->P.lambda_0;
+    return NMPM_OK;
+}
+
+int nmpm_set_stream(nmpm_handle h, void* cuda_stream) {
+    if (!h) return NMPM_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t) cuda_stream;
+    h->own_stream = false;
+    return NMPM_OK;
+}
+void* nmpm_get_stream(nmpm_handle h) { return h ? (void*) h->stream : nullptr; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// the step
+// ---------------------------------------------------------------------------------------------
+static int do_sort(nmpm_sim* h) {
+    if (h->n == 0) return NMPM_OK;
+    const uint32_t n = (uint32_t) h->n;
+    ParticleStore& S = h->store[h->cur];
+    NMPM_DISPATCH_DIM(h, (k_cell_keys<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(
+                             S, n, h->P, h->tiles_per_axis, h->sort.keys_a, nullptr, h->d_error)));
+    uint32_t *ks = nullptr, *perm = nullptr;
+    h->launches += 1 + radix_sort_pairs(h->sort, n, h->key_bits, h->stream, &ks, &perm);
+    ParticleStore& T = h->store[h->cur ^ 1];
+    NMPM_DISPATCH_DIM(h, (k_reorder<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(S, T, perm, n)));
+    h->launches++;
+    h->cur ^= 1;
+    return NMPM_OK;
+}
+
+static int do_p2g(nmpm_sim* h) {
+    CUDA_TRY(h, cudaMemsetAsync(h->grid, 0, h->cells * sizeof(float4), h->stream));
+    h->grid_valid = true;
+    if (h->n == 0) return NMPM_OK;
+    const uint32_t n = (uint32_t) h->n;
+    ParticleStore& S = h->store[h->cur];
+    int variant = h->opt.p2g_variant;
+    if (variant == 0) variant = (h->opt.sort_every > 0) ? 2 : 1;
+    if (variant == 2) {
+        NMPM_DISPATCH(h, (launch_p2g_cell<D, MODEL>(S, n, h->P, h->grid, h->d_error, h->stream)));
+    } else {
+        NMPM_DISPATCH(h, (k_p2g_scatter<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, n, h->P, h->grid,
+                                                                                            h->d_error)));
+    }
+    h->launches++;
+    return NMPM_OK;
+}
+
+static int do_grid_op(nmpm_sim* h) {
+    NMPM_DISPATCH_DIM(h, (k_grid_op<D><<<blocks_for(h->cells, 256), 256, 0, h->stream>>>(h->grid, h->cells, h->P)));
+    h->launches++;
+    return NMPM_OK;
+}
+
+static int do_g2p(nmpm_sim* h) {
+    if (h->n == 0) return NMPM_OK;
+    const uint32_t n = (uint32_t) h->n;
+    NMPM_DISPATCH(h, (k_g2p_gather<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(h->store[h->cur], n, h->P,
+                                                                                       h->grid, h->d_error)));
+    h->launches++;
+    return NMPM_OK;
+}
+
+static int run_phase(nmpm_sim* h, int phase) {
+    int rc = NMPM_OK;
+    if (phase == NMPM_PHASE_P2G) {
+        const bool sort_now = h->opt.sort_every > 0 && (h->steps_done % h->opt.sort_every) == 0;
+        if (h->timing) cudaEventRecord(h->ev[0], h->stream);
+        if (sort_now) rc = do_sort(h);
+        if (h->timing) cudaEventRecord(h->ev[1], h->stream);
+        if (rc == NMPM_OK) rc = do_p2g(h);
+        if (h->timing) cudaEventRecord(h->ev[2], h->stream);
+    } else if (phase == NMPM_PHASE_GRID_OP) {
+        rc = do_grid_op(h);
+        if (h->timing) cudaEventRecord(h->ev[3], h->stream);
+    } else {
+        rc = do_g2p(h);
+        if (h->timing) {
+            cudaEventRecord(h->ev[4], h->stream);
+            cudaEventSynchronize(h->ev[4]);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+            h->t_ms[NMPM_T_SORT] += ms;
+            cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
+            h->t_ms[NMPM_T_P2G] += ms;
+            cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+            h->t_ms[NMPM_T_GRID] += ms;
+            cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]);
+            h->t_ms[NMPM_T_G2P] += ms;
+            h->t_steps++;
+        }
+        h->steps_done++;
+    }
+    if (rc == NMPM_OK) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            h->last_error = std::string("kernel launch failed: ") + cudaGetErrorString(e);
+            rc = NMPM_ERR_CUDA;
+        }
+    }
+    return rc;
+}
+
+// non-blocking look at the error flag copied back by earlier calls
+static int poll_error(nmpm_sim* h) {
+    if (h->error_latched || (h->h_error && *((volatile int*) h->h_error) != 0)) {
+        h->error_latched = true;
+        h->last_error = "a particle's stencil left the grid (reference: std::out_of_range from vector::at, "
+                        "src/nclr.h:163)";
+        return NMPM_ERR_OUT_OF_GRID;
+    }
+    return NMPM_OK;
+}
+
+static int sync_and_check(nmpm_sim* h) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_error, h->d_error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return poll_error(h);
+}
+
+extern "C" {
+
+int nmpm_advance(nmpm_handle h, int nsteps) {
+    if (!h || nsteps < 0) return NMPM_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (int rc = poll_error(h)) return rc;
+    for (int s = 0; s < nsteps; ++s) {
+        // finish a partially executed step first (mixed nmpm_phase / nmpm_advance use)
+        for (int ph = h->phase_next; ph < 3; ++ph) {
+            if (int rc = run_phase(h, ph)) return rc;
+        }
+        h->phase_next = 0;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_error, h->d_error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    return NMPM_OK;
+}
+
+int nmpm_phase(nmpm_handle h, int phase) {
+    if (!h || phase < 0 || phase > 2) return NMPM_ERR_INVALID;
+    if (phase != h->phase_next) {
+        h->last_error = "nmpm_phase: phases must be called in order p2g, grid_op, g2p";
+        return NMPM_ERR_INVALID;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (int rc = run_phase(h, phase)) return rc;
+    h->phase_next = (phase + 1) % 3;
+    return sync_and_check(h);
+}
+
+int nmpm_synchronize(nmpm_handle h) {
+    if (!h) return NMPM_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return sync_and_check(h);
+}
+
+int nmpm_download_particles(nmpm_handle h, float* x, float* v, float* F, float* C, float* Jp) {
+    if (!h) return NMPM_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = h->n, D = (size_t) h->dim;
+    if (n) {
+        const size_t words = n * (2 * D + 2 * D * D + 1);
+        if (int rc = ensure_staging(h, words * sizeof(float))) return rc;
+        float* p = h->staging;
+        float* dx = x ? p : nullptr;
+        p += x ? n * D : 0;
+        float* dv = v ? p : nullptr;
+        p += v ? n * D : 0;
+        float* dF = F ? p : nullptr;
+        p += F ? n * D * D : 0;
+        float* dC = C ? p : nullptr;
+        p += C ? n * D * D : 0;
+        float* dJ = Jp ? p : nullptr;
+        NMPM_DISPATCH_DIM(h, (k_export_soa<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(h->store[h->cur], (uint32_t) n,
+                                                                                         dx, dv, dF, dC, dJ)));
+        h->launches++;
+        if (x) CUDA_TRY(h, cudaMemcpyAsync(x, dx, n * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        if (v) CUDA_TRY(h, cudaMemcpyAsync(v, dv, n * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        if (F) CUDA_TRY(h, cudaMemcpyAsync(F, dF, n * D * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        if (C) CUDA_TRY(h, cudaMemcpyAsync(C, dC, n * D * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        if (Jp) CUDA_TRY(h, cudaMemcpyAsync(Jp, dJ, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    }
+    return sync_and_check(h);
+}
+
+int nmpm_download_positions(nmpm_handle h, float* x) { return nmpm_download_particles(h, x, nullptr, nullptr, nullptr, nullptr); }
+
+int nmpm_download_particles_aos(nmpm_handle h, void* particles_aos, size_t stride) {
+    if (!h || !particles_aos) return NMPM_ERR_INVALID;
+    const size_t rec = (h->dim == 3) ? 112 : 64;
+    if (stride < rec || stride % 4) return NMPM_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = h->n;
+    if (n) {
+        if (int rc = ensure_staging(h, n * stride)) return rc;
+        // mass / volume / colour never change on the device: stage the caller's records so that the
+        // untouched words survive the round trip
+        CUDA_TRY(h, cudaMemcpyAsync(h->staging, particles_aos, n * stride, cudaMemcpyHostToDevice, h->stream));
+        NMPM_DISPATCH_DIM(h, (k_export_aos<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(h->store[h->cur], (uint32_t) n,
+                                                                                         h->staging, stride / 4)));
+        h->launches++;
+        CUDA_TRY(h, cudaMemcpyAsync(particles_aos, h->staging, n * stride, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return sync_and_check(h);
+}
+
+int nmpm_download_grid(nmpm_handle h, float* gv, float* gm, size_t* cells_out) {
+    if (!h) return NMPM_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (!h->grid_valid) {
+        if (cells_out) *cells_out = 0;
+        return sync_and_check(h);
+    }
+    const size_t cells = h->cells, D = (size_t) h->dim;
+    if (int rc = ensure_staging(h, cells * (D + 1) * sizeof(float))) return rc;
+    float* dgv = h->staging;
+    float* dgm = h->staging + cells * D;
+    NMPM_DISPATCH_DIM(h, (k_export_grid<D><<<blocks_for(cells, 256), 256, 0, h->stream>>>(h->grid, cells, dgv, dgm,
+                                                                                          nullptr, 0)));
+    h->launches++;
+    if (gv) CUDA_TRY(h, cudaMemcpyAsync(gv, dgv, cells * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (gm) CUDA_TRY(h, cudaMemcpyAsync(gm, dgm, cells * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (cells_out) *cells_out = cells;
+    return sync_and_check(h);
+}
+
+int nmpm_download_grid_aos(nmpm_handle h, void* cells_aos, size_t stride, size_t* cells_out) {
+    if (!h || !cells_aos) return NMPM_ERR_INVALID;
+    const size_t rec = (size_t) (h->dim + 1) * 4;
+    if (stride < rec || stride % 4) return NMPM_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (!h->grid_valid) {
+        if (cells_out) *cells_out = 0;
+        return sync_and_check(h);
+    }
+    const size_t cells = h->cells;
+    if (int rc = ensure_staging(h, cells * stride)) return rc;
+    if (stride != rec) CUDA_TRY(h, cudaMemsetAsync(h->staging, 0, cells * stride, h->stream));
+    NMPM_DISPATCH_DIM(h, (k_export_grid<D><<<blocks_for(cells, 256), 256, 0, h->stream>>>(h->grid, cells, nullptr,
+                                                                                          nullptr, h->staging,
+                                                                                          stride / 4)));
+    h->launches++;
+    CUDA_TRY(h, cudaMemcpyAsync(cells_aos, h->staging, cells * stride, cudaMemcpyDeviceToHost, h->stream));
+    if (cells_out) *cells_out = cells;
+    return sync_and_check(h);
+}
+
+int nmpm_upload_particles(nmpm_handle h, const float* x, const float* v, const float* F, const float* C,
+                          const float* Jp) {
+    if (!h || (h->n && !x)) return NMPM_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = h->n, D = (size_t) h->dim;
+    if (n == 0) return NMPM_OK;
+    const size_t words = n * (2 * D + 2 * D * D + 1);
+    if (int rc = ensure_staging(h, words * sizeof(float))) return rc;
+    float* p = h->staging;
+    cudaError_t e = cudaSuccess;
+    auto up = [&](const float* src, size_t cnt) -> float* {
+        if (!src) return nullptr;
+        float* dst = p;
+        p += cnt;
+        cudaError_t ee = cudaMemcpyAsync(dst, src, cnt * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+        if (ee != cudaSuccess) e = ee;
+        return dst;
+    };
+    float* dx = up(x, n * D);
+    float* dv = up(v, n * D);
+    float* dF = up(F, n * D * D);
+    float* dC = up(C, n * D * D);
+    float* dJ = up(Jp, n);
+    CUDA_TRY(h, e);
+    ParticleStore& S = h->store[h->cur];
+    ParticleStore& T = h->store[h->cur ^ 1];
+    // slots go back to input order: carry mass/volume over through id
+    NMPM_DISPATCH_DIM(h, (k_restore_constants<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(S, T, (uint32_t) n)));
+    NMPM_DISPATCH_DIM(h, (k_import_soa<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(dx, dv, dF, dC, dJ, nullptr,
+                                                                                     nullptr, (uint32_t) n, T, 1)));
+    h->launches += 2;
+    h->cur ^= 1;
+    h->phase_next = 0;
+    // the sort cadence restarts so that the next step re-bins the new state
+    h->steps_done = 0;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_error, 0, sizeof(int), h->stream));
+    *h->h_error = 0;
+    h->error_latched = false;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NMPM_OK;
+}
+
+int nmpm_sort_debug(nmpm_handle h, int32_t* base, uint32_t* keys_unsorted, uint32_t* keys_sorted, uint32_t* perm,
+                    uint32_t* ids) {
+    if (!h) return NMPM_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = h->n, D = (size_t) h->dim;
+    if (n == 0) return NMPM_OK;
+    if (int rc = ensure_staging(h, n * D * sizeof(int32_t))) return rc;
+    ParticleStore& S = h->store[h->cur];
+    int32_t* dbase = (int32_t*) h->staging;
+    NMPM_DISPATCH_DIM(h, (k_cell_keys<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(
+                             S, (uint32_t) n, h->P, h->tiles_per_axis, h->sort.keys_a, dbase, h->d_error)));
+    h->launches++;
+    if (base) CUDA_TRY(h, cudaMemcpyAsync(base, dbase, n * D * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (keys_unsorted)
+        CUDA_TRY(h, cudaMemcpyAsync(keys_unsorted, h->sort.keys_a, n * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                    h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    uint32_t *ks = nullptr, *pm = nullptr;
+    h->launches += radix_sort_pairs(h->sort, (uint32_t) n, h->key_bits, h->stream, &ks, &pm);
+    if (keys_sorted)
+        CUDA_TRY(h, cudaMemcpyAsync(keys_sorted, ks, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (perm) CUDA_TRY(h, cudaMemcpyAsync(perm, pm, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (ids) CUDA_TRY(h, cudaMemcpyAsync(ids, S.id, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    return NMPM_OK;
+}
+
+int nmpm_affine_debug(nmpm_handle h, float* A_out) {
+    if (!h || !A_out) return NMPM_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = h->n, D = (size_t) h->dim;
+    if (n == 0) return NMPM_OK;
+    if (int rc = ensure_staging(h, n * D * D * sizeof(float))) return rc;
+    NMPM_DISPATCH(h, (k_affine_debug<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(h->store[h->cur], (uint32_t) n,
+                                                                                         h->P, h->staging)));
+    h->launches++;
+    CUDA_TRY(h, cudaMemcpyAsync(A_out, h->staging, n * D * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    return NMPM_OK;
+}
+
+static int svd_polar_batch(int dim, size_t count, const float* A, float* U, float* sig, float* V, float* R, int device) {
+    if ((dim != 2 && dim != 3) || (count && !A)) return NMPM_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_create_error = "no CUDA device: libnmpm has no CPU fallback";
+        return NMPM_ERR_NO_DEVICE;
+    }
+    if (count == 0) return NMPM_OK;
+    nmpm_sim* h = nullptr;
+    CUDA_TRY(h, cudaSetDevice(device));
+    const size_t w = count * (size_t) (dim * dim);
+    float* d = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d, 5 * w * sizeof(float)));
+    cudaError_t e = cudaMemcpy(d, A, w * sizeof(float), cudaMemcpyHostToDevice);
+    float *dU = U ? d + w : nullptr, *dS = d + 2 * w, *dV = d + 3 * w, *dR = R ? d + 4 * w : nullptr;
+    if (e == cudaSuccess) {
+        if (dim == 2) k_svd_batch<2><<<blocks_for(count, 128), 128>>>(d, count, dU, dS, dV, dR);
+        else
+            k_svd_batch<3><<<blocks_for(count, 128), 128>>>(d, count, dU, dS, dV, dR);
+        e = cudaDeviceSynchronize();
+    }
+    if (e == cudaSuccess && U) e = cudaMemcpy(U, dU, w * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && sig) e = cudaMemcpy(sig, dS, w * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && V) e = cudaMemcpy(V, dV, w * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && R) e = cudaMemcpy(R, dR, w * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    CUDA_TRY(h, e);
+    return NMPM_OK;
+}
+
+int nmpm_svd_batch(int dim, size_t count, const float* A, float* U, float* sig, float* V, int device) {
+    if (!U || !sig || !V) return NMPM_ERR_INVALID;
+    return svd_polar_batch(dim, count, A, U, sig, V, nullptr, device);
+}
+int nmpm_polar_batch(int dim, size_t count, const float* A, float* R, int device) {
+    if (!R) return NMPM_ERR_INVALID;
+    return svd_polar_batch(dim, count, A, nullptr, nullptr, nullptr, R, device);
+}
+
+int nmpm_timing_enable(nmpm_handle h, int on) {
+    if (!h) return NMPM_ERR_INVALID;
+    h->timing = on != 0;
+    return NMPM_OK;
+}
+int nmpm_timing_read(nmpm_handle h, float* ms, int* steps, int reset) {
+    if (!h) return NMPM_ERR_INVALID;
+    if (ms) std::memcpy(ms, h->t_ms, sizeof(h->t_ms));
+    if (steps) *steps = h->t_steps;
+    if (reset) {
+        std::memset(h->t_ms, 0, sizeof(h->t_ms));
+        h->t_steps = 0;
+    }
+    return NMPM_OK;
+}
+
+
+// ---- multi-GPU slab plumbing -------------------------------------------------
+size_t nmpm_grid_plane_bytes(nmpm_handle h) {
+    if (!h) return 0;
+    const size_t n1 = (size_t) h->res + 1;
+    return (h->dim == 3 ? n1 * n1 : n1) * sizeof(float4);
+}
+void* nmpm_grid_plane_ptr(nmpm_handle h, int x_plane) {
+    if (!h || x_plane < 0 || x_plane > h->res) return nullptr;
+    return (void*) ((char*) h->grid + (size_t) x_plane * nmpm_grid_plane_bytes(h));
+}
+int nmpm_grid_add_planes(nmpm_handle h, int x_plane, int planes, const void* device_src) {
+    if (!h || !device_src || planes < 0 || x_plane < 0 || x_plane + planes > h->res + 1) return NMPM_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t count = (size_t) planes * nmpm_grid_plane_bytes(h) / sizeof(float4);
+    if (count == 0) return NMPM_OK;
+    k_add_planes<<<blocks_for(count, 256), 256, 0, h->stream>>>((float4*) nmpm_grid_plane_ptr(h, x_plane),
+                                                              (const float4*) device_src, count);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return NMPM_OK;
+}
+size_t nmpm_migrate_record_bytes(nmpm_handle h) { return h ? 28 * sizeof(float) : 0; }
+int nmpm_migrate_pack(nmpm_handle h, void** send_left, size_t* n_left, void** send_right, size_t* n_right) {
+    if (!h) return NMPM_ERR_INVALID;
+    (void) send_left, (void) n_left, (void) send_right, (void) n_right;
+    h->last_error = "nmpm_migrate_pack: particle migration is not implemented yet (single-slab sims only)";
+    return NMPM_ERR_INVALID;
+}
+int nmpm_migrate_unpack(nmpm_handle h, const void* recv_device, size_t n_recv) {
+    if (!h) return NMPM_ERR_INVALID;
+    (void) recv_device, (void) n_recv;
+    h->last_error = "nmpm_migrate_unpack: particle migration is not implemented yet (single-slab sims only)";
+    return NMPM_ERR_INVALID;
+}
+
+}  // extern "C"

@@ -1,0 +1,432 @@
+// Step kernels (sm_100a): binning keys, reorder, P2G, grid update, G2P, import/export.
+// Reference semantics: src/nclr.h:104-165 (p2g), :263-310 (grid_op), :167-261 (g2p).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "nmpm_math.cuh"
+#include "nmpm_store.cuh"
+
+namespace nmpm {
+
+// Grid node = float4 {momentum/velocity xyz, mass} (2D: {x, y, mass, 0}); dense (res+1)^dim array in
+// the reference's index order, x slowest (src/nclr.h:141-142,152).  One float4 per node makes the
+// P2G scatter a single vector reduction (RED.E.ADD.F32x4) and the G2P gather a single LDG.128.
+template <int D>
+__device__ __forceinline__ float4 node_pack(const float (&mom)[D], float m) {
+    if constexpr (D == 3) return make_float4(mom[0], mom[1], mom[2], m);
+    return make_float4(mom[0], mom[1], m, 0.0f);
+}
+
+__device__ __forceinline__ void red_add_f32x4(float4* addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+// ---- K0a: cell keys from current positions -------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) k_cell_keys(ParticleStore S, uint32_t n, MaterialParams P, int tiles_per_axis,
+                                                   uint32_t* __restrict__ keys, int32_t* __restrict__ base_out,
+                                                   int* __restrict__ error_flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x[D];
+    load_position<D>(S, i, x);
+    int b[D];
+    bool bad = false;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        b[d] = stencil_axis(x[d], P.inv_dx).base;
+        if (base_out) base_out[(size_t) i * D + d] = b[d];
+        // stencil nodes base..base+2 must lie in [0,res]  (Q5; NaN positions land here too)
+        if (!(b[d] >= 0 && b[d] + 2 <= P.res)) bad = true;
+    }
+    if (bad) {
+        atomicOr(error_flag, 1);
+        keys[i] = 0xFFFFFFFFu;
+    } else {
+        keys[i] = cell_key<D>(b, tiles_per_axis);
+    }
+}
+
+// ---- K0b: gather every particle array into sorted order -------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) k_reorder(ParticleStore src, ParticleStore dst, const uint32_t* __restrict__ perm,
+                                                 uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = perm[i];
+#pragma unroll
+    for (int k = 0; k < StoreTraits<D>::NQ; ++k) dst.q[k][i] = ldg4(src.q[k] + j);
+    dst.s[i] = __ldg(src.s + j);
+    dst.mv[i] = __ldg(src.mv + j);
+    dst.id[i] = __ldg(src.id + j);
+}
+
+template <int D>
+__device__ __forceinline__ bool stencil_of(const float (&x)[D], const MaterialParams& P, int (&base)[D], float (&fx)[D],
+                                           float (&w)[D][3]) {
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const Stencil1 s = stencil_axis(x[d], P.inv_dx);
+        base[d] = s.base;
+        fx[d] = s.fx;
+        w[d][0] = s.w[0], w[d][1] = s.w[1], w[d][2] = s.w[2];
+        if (!(s.base >= 0 && s.base + 2 <= P.res)) {
+            ok = false;
+            base[d] = min(max(s.base, 0), P.res - 2);  // keep every access in bounds; the step is flagged
+        }
+    }
+    return ok;
+}
+
+// ---- K2 (variant 1): one thread per particle, 3^D vector reductions --------------------------
+template <int D, int MODEL>
+__global__ void __launch_bounds__(128) k_p2g_scatter(ParticleStore S, uint32_t n, MaterialParams P,
+                                                     float4* __restrict__ grid, int* __restrict__ error_flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PState<D> p;
+    load_for_p2g<D>(S, i, p);
+    int base[D];
+    float fx[D], w[D][3];
+    if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
+    const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, p.mass, p.volume, P);
+    float mv[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) mv[d] = p.v[d] * p.mass;
+    const int n1 = P.n1;
+#pragma unroll
+    for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+            if constexpr (D == 3) {
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) {
+                    const float dpos[3] = {((float) ii - fx[0]) * P.dx, ((float) jj - fx[1]) * P.dx,
+                                           ((float) kk - fx[2]) * P.dx};
+                    const float weight = w[0][ii] * w[1][jj] * w[2][kk];
+                    float mom[3];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+                        mom[r] = weight * (mv[r] + (A(r, 0) * dpos[0] + A(r, 1) * dpos[1] + A(r, 2) * dpos[2]));
+                    const size_t node = ((size_t) (base[0] + ii) * n1 + (base[1] + jj)) * n1 + (base[2] + kk);
+                    red_add_f32x4(grid + node, node_pack<3>(mom, weight * p.mass));
+                }
+            } else {
+                const float dpos[2] = {((float) ii - fx[0]) * P.dx, ((float) jj - fx[1]) * P.dx};
+                const float weight = w[0][ii] * w[1][jj];
+                float mom[2];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) mom[r] = weight * (mv[r] + (A(r, 0) * dpos[0] + A(r, 1) * dpos[1]));
+                const size_t node = (size_t) (base[0] + ii) * n1 + (base[1] + jj);
+                red_add_f32x4(grid + node, node_pack<2>(mom, weight * p.mass));
+            }
+        }
+}
+
+// ---- K3: grid update (src/nclr.h:263-310) ---------------------------------------------------
+// One thread per node, float4 in / float4 out.  Normalise by mass, gravity on y (Q7), clamp to
+// ±0.9 dx/dt, then the sticky 3-node walls which zero the WHOLE node incl. its mass (Q6).
+template <int D>
+__global__ void __launch_bounds__(256) k_grid_op(float4* __restrict__ grid, size_t cells, MaterialParams P) {
+    const size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cells) return;
+    float4 g = grid[idx];
+    float vel[D];
+    float m;
+    if constexpr (D == 3) {
+        vel[0] = g.x, vel[1] = g.y, vel[2] = g.z, m = g.w;
+    } else {
+        vel[0] = g.x, vel[1] = g.y, m = g.z;
+    }
+    const bool was_zero = (m == 0.0f);
+    int c[D];
+    const int n1 = P.n1;
+    if constexpr (D == 3) {
+        c[2] = (int) (idx % n1);
+        c[1] = (int) ((idx / n1) % n1);
+        c[0] = (int) (idx / ((size_t) n1 * n1));
+    } else {
+        c[1] = (int) (idx % n1);
+        c[0] = (int) (idx / n1);
+    }
+    if (m > 0.0f) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) vel[d] = vel[d] / m;
+        vel[1] += P.dt_gravity;
+#pragma unroll
+        for (int d = 0; d < D; ++d) vel[d] = clampf(vel[d], -P.vmax, P.vmax);
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        if ((c[d] < 3 && vel[d] < 0.0f) || (c[d] >= n1 - 3 && vel[d] > 0.0f)) {
+#pragma unroll
+            for (int e = 0; e < D; ++e) vel[e] = 0.0f;
+            m = 0.0f;
+        }
+    }
+    if (was_zero && m == 0.0f) {
+        bool all_zero = true;
+#pragma unroll
+        for (int d = 0; d < D; ++d) all_zero = all_zero && (vel[d] == 0.0f);
+        if (all_zero) return;  // untouched empty node: nothing to write back
+    }
+    grid[idx] = node_pack<D>(vel, m);
+}
+
+// ---- K4: G2P (src/nclr.h:167-261) -------------------------------------------------------------
+template <int D, int MODEL>
+__device__ __forceinline__ void g2p_update(PState<D>& p, const Mat<D>& Cn, const float (&vn)[D], const MaterialParams& P) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        p.v[d] = vn[d];
+        p.x[d] = fmaf(P.dt, vn[d], p.x[d]);  // advection (src/nclr.h:229)
+    }
+    p.C = Cn;
+    // F' = (diag<dim>(1) + dt*C) * F   (Q1: the "identity" has a zero (2,2) entry in 3D)
+    Mat<D> M;
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) M.m[k] = P.dt * Cn.m[k];
+    M(0, 0) += 1.0f;
+    M(1, 1) += 1.0f;
+    Mat<D> Fn = mat_mul<D>(M, p.F);
+    if constexpr (MODEL == 1) {  // jelly (src/nclr.h:232-234)
+        p.F = Fn;
+    } else {
+        Mat<D> U, V;
+        float sig[D];
+        nclr_svd<D>(Fn, U, sig, V);
+        if constexpr (MODEL == 0) {  // snow plasticity (src/nclr.h:239-250)
+#pragma unroll
+            for (int d = 0; d < D; ++d) sig[d] = clampf(sig[d], 0.975f, 1.0045f);
+            const float old_J = det(Fn);
+            Mat<D> Us;
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+#pragma unroll
+                for (int i = 0; i < D; ++i) Us(i, j) = U(i, j) * sig[j];
+            Fn = mat_mul_bt<D>(Us, V);
+            p.Jp = clampf(p.Jp * old_J / det(Fn), 0.6f, 20.0f);
+            p.F = Fn;
+        } else {  // liquid (src/nclr.h:252-258): J in double, F = diag<dim>(1) with F(0,0) = J
+            double J = 1.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) J *= (double) sig[d];
+#pragma unroll
+            for (int k = 0; k < D * D; ++k) p.F.m[k] = 0.0f;
+            p.F(1, 1) = 1.0f;
+            p.F(0, 0) = (float) J;
+        }
+    }
+}
+
+template <int D, int MODEL>
+__global__ void __launch_bounds__(128) k_g2p_gather(ParticleStore S, uint32_t n, MaterialParams P,
+                                                    const float4* __restrict__ grid, int* __restrict__ error_flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PState<D> p;
+    load_for_g2p<D>(S, i, p);
+    int base[D];
+    float fx[D], w[D][3];
+    if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
+    float vn[D];
+    Mat<D> Cn;
+#pragma unroll
+    for (int d = 0; d < D; ++d) vn[d] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) Cn.m[k] = 0.0f;
+    const int n1 = P.n1;
+    const float four_inv_dx = 4.0f * P.inv_dx;
+#pragma unroll
+    for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+            if constexpr (D == 3) {
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) {
+                    const size_t node = ((size_t) (base[0] + ii) * n1 + (base[1] + jj)) * n1 + (base[2] + kk);
+                    const float4 g = ldg4(grid + node);
+                    const float weight = w[0][ii] * w[1][jj] * w[2][kk];
+                    const float dpos[3] = {(float) ii - fx[0], (float) jj - fx[1], (float) kk - fx[2]};
+                    const float gv[3] = {g.x, g.y, g.z};
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const float wv = weight * gv[r];
+                        vn[r] += wv;
+                        const float t = four_inv_dx * wv;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) Cn(r, c) = fmaf(t, dpos[c], Cn(r, c));
+                    }
+                }
+            } else {
+                const size_t node = (size_t) (base[0] + ii) * n1 + (base[1] + jj);
+                const float4 g = ldg4(grid + node);
+                const float weight = w[0][ii] * w[1][jj];
+                const float dpos[2] = {(float) ii - fx[0], (float) jj - fx[1]};
+                const float gv[2] = {g.x, g.y};
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const float wv = weight * gv[r];
+                    vn[r] += wv;
+                    const float t = four_inv_dx * wv;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) Cn(r, c) = fmaf(t, dpos[c], Cn(r, c));
+                }
+            }
+        }
+    g2p_update<D, MODEL>(p, Cn, vn, P);
+    store_state<D>(S, i, p);
+}
+
+// ---- K5: import / export between the interchange layouts and the device store ---------------
+// AoS record = the reference's Particle<dim> (src/nclr.h:20-48): x, v, F, C, Jp, mass, volume, c
+//   2D: 16 words (64 B), 3D: 28 words (112 B).  stride_w = record stride in 4-byte words.
+template <int D>
+__global__ void __launch_bounds__(256) k_import_aos(const float* __restrict__ aos, size_t stride_w, uint32_t n,
+                                                    ParticleStore S) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = aos + (size_t) i * stride_w;
+    PState<D> p;
+#pragma unroll
+    for (int d = 0; d < D; ++d) p.x[d] = r[d], p.v[d] = r[D + d];
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) p.F.m[k] = r[2 * D + k], p.C.m[k] = r[2 * D + D * D + k];
+    p.Jp = r[2 * D + 2 * D * D];
+    store_state<D>(S, i, p);
+    S.mv[i] = make_float2(r[2 * D + 2 * D * D + 1], r[2 * D + 2 * D * D + 2]);
+    S.id[i] = i;
+}
+
+// writes x, v, F, C, Jp of slot i into record id[i] (input order); mass/volume/c are left untouched
+template <int D>
+__global__ void __launch_bounds__(256) k_export_aos(ParticleStore S, uint32_t n, float* __restrict__ aos,
+                                                    size_t stride_w) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PState<D> p;
+    load_for_p2g<D>(S, i, p);
+    float* r = aos + (size_t) S.id[i] * stride_w;
+#pragma unroll
+    for (int d = 0; d < D; ++d) r[d] = p.x[d], r[D + d] = p.v[d];
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) r[2 * D + k] = p.F.m[k], r[2 * D + D * D + k] = p.C.m[k];
+    r[2 * D + 2 * D * D] = p.Jp;
+}
+
+// SoA interchange arrays (any may be null on import => reference defaults, src/nclr.h:46-47)
+template <int D>
+__global__ void __launch_bounds__(256) k_import_soa(const float* __restrict__ x, const float* __restrict__ v,
+                                                    const float* __restrict__ F, const float* __restrict__ C,
+                                                    const float* __restrict__ Jp, const float* __restrict__ mass,
+                                                    const float* __restrict__ volume, uint32_t n, ParticleStore S,
+                                                    int keep_constants) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PState<D> p;
+#pragma unroll
+    for (int d = 0; d < D; ++d) p.x[d] = x[(size_t) i * D + d], p.v[d] = v ? v[(size_t) i * D + d] : 0.0f;
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) {
+        p.F.m[k] = F ? F[(size_t) i * D * D + k] : 0.0f;
+        p.C.m[k] = C ? C[(size_t) i * D * D + k] : 0.0f;
+    }
+    if (!F) p.F(0, 0) = 1.0f, p.F(1, 1) = 1.0f;  // diag<dim>(1): Q1
+    p.Jp = Jp ? Jp[i] : 1.0f;
+    store_state<D>(S, i, p);
+    if (!keep_constants) S.mv[i] = make_float2(mass ? mass[i] : 1.0f, volume ? volume[i] : 1.0f);
+    S.id[i] = i;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_export_soa(ParticleStore S, uint32_t n, float* __restrict__ x,
+                                                    float* __restrict__ v, float* __restrict__ F, float* __restrict__ C,
+                                                    float* __restrict__ Jp) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PState<D> p;
+    load_for_p2g<D>(S, i, p);
+    const size_t o = S.id[i];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        if (x) x[o * D + d] = p.x[d];
+        if (v) v[o * D + d] = p.v[d];
+    }
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) {
+        if (F) F[o * D * D + k] = p.F.m[k];
+        if (C) C[o * D * D + k] = p.C.m[k];
+    }
+    if (Jp) Jp[o] = p.Jp;
+}
+
+// When slots must return to input order (upload of a new state keeps mass/volume): inverse of id
+template <int D>
+__global__ void __launch_bounds__(256) k_restore_constants(ParticleStore src, ParticleStore dst, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst.mv[src.id[i]] = src.mv[i];
+}
+
+// grid export: float4 nodes -> (gv, gm) SoA or Cell<dim> AoS (src/nclr.h:50-55: velocity then mass)
+template <int D>
+__global__ void __launch_bounds__(256) k_export_grid(const float4* __restrict__ grid, size_t cells, float* __restrict__ gv,
+                                                     float* __restrict__ gm, float* __restrict__ aos, size_t stride_w) {
+    const size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cells) return;
+    const float4 g = grid[idx];
+    const float vel[3] = {g.x, g.y, g.z};
+    const float m = (D == 3) ? g.w : g.z;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        if (gv) gv[idx * D + d] = vel[d];
+        if (aos) aos[idx * stride_w + d] = vel[d];
+    }
+    if (gm) gm[idx] = m;
+    if (aos) aos[idx * stride_w + D] = m;
+}
+
+// ---- unit hooks -------------------------------------------------------------------------------
+template <int D>
+__global__ void k_svd_batch(const float* __restrict__ A, size_t count, float* __restrict__ U, float* __restrict__ S,
+                            float* __restrict__ V, float* __restrict__ R) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Mat<D> a, u, v;
+    float sig[D];
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) a.m[k] = A[i * D * D + k];
+    if (R) {
+        const Mat<D> r = nclr_polar_R(a);
+#pragma unroll
+        for (int k = 0; k < D * D; ++k) R[i * D * D + k] = r.m[k];
+    }
+    if (U) {
+        nclr_svd<D>(a, u, sig, v);
+#pragma unroll
+        for (int k = 0; k < D * D; ++k) {
+            U[i * D * D + k] = u.m[k];
+            V[i * D * D + k] = v.m[k];
+            S[i * D * D + k] = 0.0f;
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) S[i * D * D + d + d * D] = sig[d];
+    }
+}
+
+template <int D, int MODEL>
+__global__ void k_affine_debug(ParticleStore S, uint32_t n, MaterialParams P, float* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PState<D> p;
+    load_for_p2g<D>(S, i, p);
+    const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, p.mass, p.volume, P);
+    const size_t o = S.id[i];
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) out[o * D * D + k] = A.m[k];
+}
+
+}  // namespace nmpm

@@ -1,0 +1,308 @@
+"""Python mirror of the reference's solver interface over the C-ABI (include/nmpm.h).
+
+Reference surface mirrored (same names, argument meaning and error behaviour):
+  nclr::MaterialModel                          src/nclr.h:57-61
+  nclr::MPMSimulation<dim>(particles, model, res=64, dt=1e-4, E=1e4, nu=0.2, gravity=-100)
+                                               src/nclr.h:74-78
+  advance(), particles(), grid(), mu_0, lambda_0, kBoundary, k*Hardening
+                                               src/nclr.h:66-72,80-87
+  nclr::cube<dim>(res, min, max)               src/nclr_math.h:100-129
+Out-of-grid particles raise OutOfGridError (an IndexError), the analogue of the std::out_of_range the
+reference throws from vector::at (src/nclr.h:163).
+
+numpy conventions: x,v (n,dim); F,C (n,dim,dim) stored per particle column-major like Eigen, i.e.
+``F[p, j, i]`` is F(i,j); Jp,mass,volume (n,).  Grid: (cells,dim) velocity and (cells,) mass in the
+reference's node order (x slowest).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+_fp = C.POINTER(C.c_float)
+_u32p = C.POINTER(C.c_uint32)
+_i32p = C.POINTER(C.c_int32)
+NMPM_T_COUNT = 8
+
+
+class NmpmError(RuntimeError):
+    pass
+
+
+class OutOfGridError(IndexError):
+    """A particle's stencil left the grid (reference: std::out_of_range, src/nclr.h:163; Q5)."""
+
+
+class MaterialModel(enum.IntEnum):
+    kSnow = 0
+    kJelly = 1
+    kLiquid = 2
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int), ("sort_every", C.c_int), ("p2g_variant", C.c_int), ("use_graph", C.c_int),
+                ("slab_x0", C.c_int), ("slab_x1", C.c_int), ("reserved", C.c_int * 10)]
+
+
+def lib_path() -> Path:
+    return _PKG / "lib" / "libnmpm.so"
+
+
+_lib = None
+
+
+def load_library():
+    """Load libnmpm.so; fails loudly when it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not p.exists():
+        raise NmpmError(f"{p} is missing: build it with `python -m nuclearmpm_b200.build` (nvcc, sm_100a). "
+                        "There is no CPU fallback.")
+    L = C.CDLL(str(p))
+    vp, sz, ci, cf = C.c_void_p, C.c_size_t, C.c_int, C.c_float
+
+    def sig(name, res, args):
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+
+    sig("nmpm_default_options", None, [C.POINTER(Options)])
+    sig("nmpm_create", ci, [ci, ci, ci, cf, cf, cf, cf, sz] + [_fp] * 7 + [C.POINTER(Options), C.POINTER(vp)])
+    sig("nmpm_create_aos", ci, [ci, ci, ci, cf, cf, cf, cf, sz, vp, sz, C.POINTER(Options), C.POINTER(vp)])
+    sig("nmpm_destroy", None, [vp])
+    sig("nmpm_advance", ci, [vp, ci])
+    sig("nmpm_phase", ci, [vp, ci])
+    sig("nmpm_synchronize", ci, [vp])
+    sig("nmpm_download_particles", ci, [vp] + [_fp] * 5)
+    sig("nmpm_download_particles_aos", ci, [vp, vp, sz])
+    sig("nmpm_download_positions", ci, [vp, _fp])
+    sig("nmpm_download_grid", ci, [vp, _fp, _fp, C.POINTER(sz)])
+    sig("nmpm_download_grid_aos", ci, [vp, vp, sz, C.POINTER(sz)])
+    sig("nmpm_upload_particles", ci, [vp] + [_fp] * 5)
+    sig("nmpm_num_particles", sz, [vp])
+    sig("nmpm_grid_cells", sz, [vp])
+    sig("nmpm_lame", ci, [vp, _fp, _fp])
+    sig("nmpm_sort_debug", ci, [vp, _i32p, _u32p, _u32p, _u32p, _u32p])
+    sig("nmpm_key_tile_bits", ci, [vp])
+    sig("nmpm_svd_batch", ci, [ci, sz, _fp, _fp, _fp, _fp, ci])
+    sig("nmpm_polar_batch", ci, [ci, sz, _fp, _fp, ci])
+    sig("nmpm_affine_debug", ci, [vp, _fp])
+    sig("nmpm_timing_enable", ci, [vp, ci])
+    sig("nmpm_timing_read", ci, [vp, _fp, C.POINTER(ci), ci])
+    sig("nmpm_launch_count", C.c_longlong, [vp])
+    sig("nmpm_set_stream", ci, [vp, vp])
+    sig("nmpm_get_stream", vp, [vp])
+    sig("nmpm_grid_plane_ptr", vp, [vp, ci])
+    sig("nmpm_grid_plane_bytes", sz, [vp])
+    sig("nmpm_grid_add_planes", ci, [vp, ci, ci, vp])
+    sig("nmpm_migrate_pack", ci, [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)])
+    sig("nmpm_migrate_unpack", ci, [vp, vp, sz])
+    sig("nmpm_migrate_record_bytes", sz, [vp])
+    sig("nmpm_last_error", C.c_char_p, [vp])
+    sig("nmpm_build_info", C.c_char_p, [])
+    _lib = L
+    return L
+
+
+def _f32(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a.reshape(shape) if shape is not None else a
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_fp)
+
+
+def cube(dim: int, res: int, lo: float, hi: float) -> np.ndarray:
+    """nclr::cube<dim>(res, min, max) (src/nclr_math.h:100-129): res**dim points, x slowest, built
+    from Eigen's LinSpaced rule in fp32 (step=(hi-lo)/(res-1); last value pinned to hi, or — when
+    |hi| < |lo| — first value pinned to lo and the rest counted back from hi)."""
+    lo32, hi32 = np.float32(lo), np.float32(hi)
+    i = np.arange(res, dtype=np.float32)
+    if res == 1:
+        axis = np.array([lo32], np.float32)  # Eigen: size1 = 1, so i == 0 takes the `low + i*step` branch
+    else:
+        step = np.float32((hi32 - lo32) / np.float32(res - 1))
+        if abs(hi32) < abs(lo32):
+            axis = (hi32 - (np.float32(res - 1) - i) * step).astype(np.float32)
+            axis[0] = lo32
+        else:
+            axis = (lo32 + i * step).astype(np.float32)
+            axis[-1] = hi32
+    g = np.meshgrid(*([axis] * dim), indexing="ij")
+    return np.stack([a.ravel() for a in g], axis=1).astype(np.float32)
+
+
+class MPMSimulation:
+    """GPU MPMSimulation<dim>.  `particles` is an (n,dim) float32 position array (dim = 2 or 3)."""
+
+    kBoundary = 3            # src/nclr.h:66
+    kSnowHardening = 10.0    # src/nclr.h:67
+    kJellyHardening = 0.3    # src/nclr.h:68
+    kLiquidHardening = 1.0   # src/nclr.h:69
+
+    def __init__(self, particles, model, res: int = 64, dt: float = 1e-4, E: float = 1e4, nu: float = 0.2,
+                 gravity: float = -100.0, *, v=None, F=None, C=None, Jp=None, mass=None, volume=None,
+                 device: int = 0, sort_every: int = 1, p2g_variant: int = 0, slab=None):
+        self._L = load_library()
+        x = _f32(particles)
+        if x.ndim != 2 or x.shape[1] not in (2, 3):
+            raise ValueError("particles must be an (n, 2) or (n, 3) array of positions")
+        self.n, self.dim = x.shape
+        self.res, self.model = int(res), MaterialModel(int(model))
+        n, d = self.n, self.dim
+        opt = Options()
+        self._L.nmpm_default_options(C_byref(opt))
+        opt.device, opt.sort_every, opt.p2g_variant = device, sort_every, p2g_variant
+        if slab is not None:
+            opt.slab_x0, opt.slab_x1 = slab
+        arrs = [x, _f32(v, (n, d)), _f32(F, (n, d, d)), _f32(C, (n, d, d)), _f32(Jp, (n,)), _f32(mass, (n,)),
+                _f32(volume, (n,))]
+        h = C_void_p()
+        rc = self._L.nmpm_create(d, int(model), int(res), dt, E, nu, gravity, n, *[_p(a) for a in arrs],
+                                 C_byref(opt), C_byref(h))
+        if rc != 0:
+            raise NmpmError(f"nmpm_create failed ({rc}): {self._L.nmpm_last_error(None).decode()}")
+        self._h = h
+        mu, lam = C.c_float(), C.c_float()
+        self._L.nmpm_lame(self._h, C_byref(mu), C_byref(lam))
+        self.mu_0, self.lambda_0 = mu.value, lam.value
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.nmpm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc == 0:
+            return
+        msg = self._L.nmpm_last_error(self._h).decode()
+        if rc == 3:
+            raise OutOfGridError(msg)
+        raise NmpmError(f"{what} failed ({rc}): {msg}")
+
+    # -- the reference's interface ----------------------------------------------------------------
+    def advance(self, nsteps: int = 1, sync: bool = False) -> None:
+        """advance() × nsteps (src/nclr.h:80-84).  Asynchronous; errors surface at the next sync."""
+        self._check(self._L.nmpm_advance(self._h, int(nsteps)), "nmpm_advance")
+        if sync:
+            self.synchronize()
+
+    def synchronize(self) -> None:
+        self._check(self._L.nmpm_synchronize(self._h), "nmpm_synchronize")
+
+    def particles(self) -> dict:
+        """particles() (src/nclr.h:86): state in INPUT order."""
+        n, d = self.n, self.dim
+        out = dict(x=np.empty((n, d), np.float32), v=np.empty((n, d), np.float32),
+                   F=np.empty((n, d, d), np.float32), C=np.empty((n, d, d), np.float32),
+                   Jp=np.empty((n,), np.float32))
+        self._check(self._L.nmpm_download_particles(self._h, *[_p(out[k]) for k in ("x", "v", "F", "C", "Jp")]),
+                    "nmpm_download_particles")
+        return out
+
+    def positions(self) -> np.ndarray:
+        x = np.empty((self.n, self.dim), np.float32)
+        self._check(self._L.nmpm_download_positions(self._h, _p(x)), "nmpm_download_positions")
+        return x
+
+    def grid(self):
+        """grid() (src/nclr.h:87): (velocity (cells,dim), mass (cells,)); empty before the first step."""
+        cells = (self.res + 1) ** self.dim
+        gv = np.empty((cells, self.dim), np.float32)
+        gm = np.empty((cells,), np.float32)
+        got = C.c_size_t(0)
+        self._check(self._L.nmpm_download_grid(self._h, _p(gv), _p(gm), C_byref(got)), "nmpm_download_grid")
+        if got.value == 0:
+            return gv[:0], gm[:0]
+        return gv, gm
+
+    # -- test / profiling hooks ---------------------------------------------------------------------
+    def phase(self, which: int) -> None:
+        self._check(self._L.nmpm_phase(self._h, int(which)), "nmpm_phase")
+
+    def upload(self, x, v=None, F=None, C=None, Jp=None) -> None:
+        n, d = self.n, self.dim
+        arrs = [_f32(x, (n, d)), _f32(v, (n, d)), _f32(F, (n, d, d)), _f32(C, (n, d, d)), _f32(Jp, (n,))]
+        self._check(self._L.nmpm_upload_particles(self._h, *[_p(a) for a in arrs]), "nmpm_upload_particles")
+
+    def sort_debug(self) -> dict:
+        n, d = self.n, self.dim
+        out = dict(base=np.empty((n, d), np.int32), keys=np.empty(n, np.uint32), keys_sorted=np.empty(n, np.uint32),
+                   perm=np.empty(n, np.uint32), ids=np.empty(n, np.uint32))
+        self._check(self._L.nmpm_sort_debug(self._h, out["base"].ctypes.data_as(_i32p),
+                                            out["keys"].ctypes.data_as(_u32p),
+                                            out["keys_sorted"].ctypes.data_as(_u32p),
+                                            out["perm"].ctypes.data_as(_u32p), out["ids"].ctypes.data_as(_u32p)),
+                    "nmpm_sort_debug")
+        out["tile_bits"] = int(self._L.nmpm_key_tile_bits(self._h))
+        return out
+
+    def affine(self) -> np.ndarray:
+        A = np.empty((self.n, self.dim, self.dim), np.float32)
+        self._check(self._L.nmpm_affine_debug(self._h, _p(A)), "nmpm_affine_debug")
+        return A
+
+    def timing_enable(self, on: bool = True) -> None:
+        self._L.nmpm_timing_enable(self._h, int(on))
+
+    def timing_read(self, reset: bool = True):
+        ms = (C.c_float * NMPM_T_COUNT)()
+        steps = C.c_int(0)
+        self._L.nmpm_timing_read(self._h, ms, C_byref(steps), int(reset))
+        return dict(sort=ms[0], p2g=ms[1], grid=ms[2], g2p=ms[3], steps=steps.value)
+
+    def launch_count(self) -> int:
+        return int(self._L.nmpm_launch_count(self._h))
+
+    def set_stream(self, cuda_stream: int) -> None:
+        self._check(self._L.nmpm_set_stream(self._h, C.c_void_p(cuda_stream)), "nmpm_set_stream")
+
+    @property
+    def stream(self) -> int:
+        return int(self._L.nmpm_get_stream(self._h) or 0)
+
+
+def C_byref(x):
+    return C.byref(x)
+
+
+def C_void_p():
+    return C.c_void_p()
+
+
+def svd_batch(A: np.ndarray, device: int = 0):
+    """Device nclr_svd (src/nclr_math.h:50-74) on a batch of column-major matrices (k,dim,dim)."""
+    L = load_library()
+    A = _f32(A)
+    k, d, _ = A.shape
+    U, S, V = (np.empty_like(A) for _ in range(3))
+    rc = L.nmpm_svd_batch(d, k, _p(A), _p(U), _p(S), _p(V), device)
+    if rc:
+        raise NmpmError(f"nmpm_svd_batch failed ({rc}): {L.nmpm_last_error(None).decode()}")
+    return U, S, V
+
+
+def polar_batch(A: np.ndarray, device: int = 0) -> np.ndarray:
+    L = load_library()
+    A = _f32(A)
+    k, d, _ = A.shape
+    R = np.empty_like(A)
+    rc = L.nmpm_polar_batch(d, k, _p(A), _p(R), device)
+    if rc:
+        raise NmpmError(f"nmpm_polar_batch failed ({rc}): {L.nmpm_last_error(None).decode()}")
+    return R
