@@ -36,10 +36,10 @@ __global__ void __launch_bounds__(256) k_cell_keys(ParticleStore S, uint32_t n, 
     bool bad = false;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-        b[d] = stencil_axis(x[d], P.inv_dx).base;
+        const Stencil1 s = stencil_axis(x[d], P.inv_dx, P.res);
+        b[d] = s.base;
         if (base_out) base_out[(size_t) i * D + d] = b[d];
-        // stencil nodes base..base+2 must lie in [0,res]  (Q5; NaN positions land here too)
-        if (!(b[d] >= 0 && b[d] + 2 <= P.res)) bad = true;
+        if (!s.ok) bad = true;  // stencil left [0,res] (Q5) or x is not finite
     }
     if (bad) {
         atomicOr(error_flag, 1);
@@ -69,11 +69,11 @@ __device__ __forceinline__ bool stencil_of(const float (&x)[D], const MaterialPa
     bool ok = true;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-        const Stencil1 s = stencil_axis(x[d], P.inv_dx);
+        const Stencil1 s = stencil_axis(x[d], P.inv_dx, P.res);
         base[d] = s.base;
         fx[d] = s.fx;
         w[d][0] = s.w[0], w[d][1] = s.w[1], w[d][2] = s.w[2];
-        if (!(s.base >= 0 && s.base + 2 <= P.res)) {
+        if (!s.ok) {
             ok = false;
             base[d] = min(max(s.base, 0), P.res - 2);  // keep every access in bounds; the step is flagged
         }

@@ -307,13 +307,18 @@ struct Stencil1 {
     int base;
     float fx;
     float w[3];
+    bool ok;  // stencil nodes base..base+2 inside [0,res] and x finite
 };
-__device__ __forceinline__ Stencil1 stencil_axis(float x, float inv_dx) {
+__device__ __forceinline__ Stencil1 stencil_axis(float x, float inv_dx, int res) {
     Stencil1 s;
     // __fmul_rn / __fsub_rn: no FMA contraction, so base and fx are bit-identical to the strict-FP
     // reference for any res, not only powers of two (Q10)
     const float g = __fmul_rn(x, inv_dx);
-    s.base = (int) __fsub_rn(g, 0.5f);  // cast<int>: truncation toward zero (Q4)
+    const float t = __fsub_rn(g, 0.5f);
+    s.base = (int) t;  // cast<int>: truncation toward zero (Q4)
+    // base >= 0 && base+2 <= res, written on the float so that NaN / inf fail too.  (The reference
+    // converts NaN to INT_MIN on x86 and throws from vector::at; CUDA's cvt would give 0.)
+    s.ok = (t > -1.0f) && (t < (float) (res - 1));
     s.fx = __fsub_rn(g, (float) s.base);
     const float a = 1.5f - s.fx, b = s.fx - 1.0f, c = s.fx - 0.5f;
     s.w[0] = 0.5f * (a * a);

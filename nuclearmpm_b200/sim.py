@@ -16,16 +16,16 @@ reference's node order (x slowest).
 """
 from __future__ import annotations
 
-import ctypes as C
+import ctypes as ct
 import enum
 from pathlib import Path
 
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-_fp = C.POINTER(C.c_float)
-_u32p = C.POINTER(C.c_uint32)
-_i32p = C.POINTER(C.c_int32)
+_fp = ct.POINTER(ct.c_float)
+_u32p = ct.POINTER(ct.c_uint32)
+_i32p = ct.POINTER(ct.c_int32)
 NMPM_T_COUNT = 8
 
 
@@ -43,9 +43,9 @@ class MaterialModel(enum.IntEnum):
     kLiquid = 2
 
 
-class Options(C.Structure):
-    _fields_ = [("device", C.c_int), ("sort_every", C.c_int), ("p2g_variant", C.c_int), ("use_graph", C.c_int),
-                ("slab_x0", C.c_int), ("slab_x1", C.c_int), ("reserved", C.c_int * 10)]
+class Options(ct.Structure):
+    _fields_ = [("device", ct.c_int), ("sort_every", ct.c_int), ("p2g_variant", ct.c_int), ("use_graph", ct.c_int),
+                ("slab_x0", ct.c_int), ("slab_x1", ct.c_int), ("reserved", ct.c_int * 10)]
 
 
 def lib_path() -> Path:
@@ -64,16 +64,16 @@ def load_library():
     if not p.exists():
         raise NmpmError(f"{p} is missing: build it with `python -m nuclearmpm_b200.build` (nvcc, sm_100a). "
                         "There is no CPU fallback.")
-    L = C.CDLL(str(p))
-    vp, sz, ci, cf = C.c_void_p, C.c_size_t, C.c_int, C.c_float
+    L = ct.CDLL(str(p))
+    vp, sz, ci, cf = ct.c_void_p, ct.c_size_t, ct.c_int, ct.c_float
 
     def sig(name, res, args):
         f = getattr(L, name)
         f.restype, f.argtypes = res, args
 
-    sig("nmpm_default_options", None, [C.POINTER(Options)])
-    sig("nmpm_create", ci, [ci, ci, ci, cf, cf, cf, cf, sz] + [_fp] * 7 + [C.POINTER(Options), C.POINTER(vp)])
-    sig("nmpm_create_aos", ci, [ci, ci, ci, cf, cf, cf, cf, sz, vp, sz, C.POINTER(Options), C.POINTER(vp)])
+    sig("nmpm_default_options", None, [ct.POINTER(Options)])
+    sig("nmpm_create", ci, [ci, ci, ci, cf, cf, cf, cf, sz] + [_fp] * 7 + [ct.POINTER(Options), ct.POINTER(vp)])
+    sig("nmpm_create_aos", ci, [ci, ci, ci, cf, cf, cf, cf, sz, vp, sz, ct.POINTER(Options), ct.POINTER(vp)])
     sig("nmpm_destroy", None, [vp])
     sig("nmpm_advance", ci, [vp, ci])
     sig("nmpm_phase", ci, [vp, ci])
@@ -81,8 +81,8 @@ def load_library():
     sig("nmpm_download_particles", ci, [vp] + [_fp] * 5)
     sig("nmpm_download_particles_aos", ci, [vp, vp, sz])
     sig("nmpm_download_positions", ci, [vp, _fp])
-    sig("nmpm_download_grid", ci, [vp, _fp, _fp, C.POINTER(sz)])
-    sig("nmpm_download_grid_aos", ci, [vp, vp, sz, C.POINTER(sz)])
+    sig("nmpm_download_grid", ci, [vp, _fp, _fp, ct.POINTER(sz)])
+    sig("nmpm_download_grid_aos", ci, [vp, vp, sz, ct.POINTER(sz)])
     sig("nmpm_upload_particles", ci, [vp] + [_fp] * 5)
     sig("nmpm_num_particles", sz, [vp])
     sig("nmpm_grid_cells", sz, [vp])
@@ -93,18 +93,18 @@ def load_library():
     sig("nmpm_polar_batch", ci, [ci, sz, _fp, _fp, ci])
     sig("nmpm_affine_debug", ci, [vp, _fp])
     sig("nmpm_timing_enable", ci, [vp, ci])
-    sig("nmpm_timing_read", ci, [vp, _fp, C.POINTER(ci), ci])
-    sig("nmpm_launch_count", C.c_longlong, [vp])
+    sig("nmpm_timing_read", ci, [vp, _fp, ct.POINTER(ci), ci])
+    sig("nmpm_launch_count", ct.c_longlong, [vp])
     sig("nmpm_set_stream", ci, [vp, vp])
     sig("nmpm_get_stream", vp, [vp])
     sig("nmpm_grid_plane_ptr", vp, [vp, ci])
     sig("nmpm_grid_plane_bytes", sz, [vp])
     sig("nmpm_grid_add_planes", ci, [vp, ci, ci, vp])
-    sig("nmpm_migrate_pack", ci, [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)])
+    sig("nmpm_migrate_pack", ci, [vp, ct.POINTER(vp), ct.POINTER(sz), ct.POINTER(vp), ct.POINTER(sz)])
     sig("nmpm_migrate_unpack", ci, [vp, vp, sz])
     sig("nmpm_migrate_record_bytes", sz, [vp])
-    sig("nmpm_last_error", C.c_char_p, [vp])
-    sig("nmpm_build_info", C.c_char_p, [])
+    sig("nmpm_last_error", ct.c_char_p, [vp])
+    sig("nmpm_build_info", ct.c_char_p, [])
     _lib = L
     return L
 
@@ -171,7 +171,7 @@ class MPMSimulation:
         if rc != 0:
             raise NmpmError(f"nmpm_create failed ({rc}): {self._L.nmpm_last_error(None).decode()}")
         self._h = h
-        mu, lam = C.c_float(), C.c_float()
+        mu, lam = ct.c_float(), ct.c_float()
         self._L.nmpm_lame(self._h, C_byref(mu), C_byref(lam))
         self.mu_0, self.lambda_0 = mu.value, lam.value
 
@@ -225,7 +225,7 @@ class MPMSimulation:
         cells = (self.res + 1) ** self.dim
         gv = np.empty((cells, self.dim), np.float32)
         gm = np.empty((cells,), np.float32)
-        got = C.c_size_t(0)
+        got = ct.c_size_t(0)
         self._check(self._L.nmpm_download_grid(self._h, _p(gv), _p(gm), C_byref(got)), "nmpm_download_grid")
         if got.value == 0:
             return gv[:0], gm[:0]
@@ -261,8 +261,8 @@ class MPMSimulation:
         self._L.nmpm_timing_enable(self._h, int(on))
 
     def timing_read(self, reset: bool = True):
-        ms = (C.c_float * NMPM_T_COUNT)()
-        steps = C.c_int(0)
+        ms = (ct.c_float * NMPM_T_COUNT)()
+        steps = ct.c_int(0)
         self._L.nmpm_timing_read(self._h, ms, C_byref(steps), int(reset))
         return dict(sort=ms[0], p2g=ms[1], grid=ms[2], g2p=ms[3], steps=steps.value)
 
@@ -270,7 +270,7 @@ class MPMSimulation:
         return int(self._L.nmpm_launch_count(self._h))
 
     def set_stream(self, cuda_stream: int) -> None:
-        self._check(self._L.nmpm_set_stream(self._h, C.c_void_p(cuda_stream)), "nmpm_set_stream")
+        self._check(self._L.nmpm_set_stream(self._h, ct.c_void_p(cuda_stream)), "nmpm_set_stream")
 
     @property
     def stream(self) -> int:
@@ -278,11 +278,11 @@ class MPMSimulation:
 
 
 def C_byref(x):
-    return C.byref(x)
+    return ct.byref(x)
 
 
 def C_void_p():
-    return C.c_void_p()
+    return ct.c_void_p()
 
 
 def svd_batch(A: np.ndarray, device: int = 0):
