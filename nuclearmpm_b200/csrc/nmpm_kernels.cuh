@@ -232,14 +232,17 @@ __global__ void __launch_bounds__(128) k_g2p_gather(ParticleStore S, uint32_t n,
     int base[D];
     float fx[D], w[D][3];
     if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
-    float vn[D];
-    Mat<D> Cn;
-#pragma unroll
-    for (int d = 0; d < D; ++d) vn[d] = 0.0f;
-#pragma unroll
-    for (int k = 0; k < D * D; ++k) Cn.m[k] = 0.0f;
+    // Gather with the stencil offsets centred on the middle node:  o = ijk - 1 in {-1,0,+1},
+    //   v   = sum w g
+    //   B_c = sum w g o_c                  (adds/subtracts only: the o_c = 0 terms vanish at compile time)
+    //   C   = 4 inv_dx (B - v (fx-1)^T)    == sum 4 inv_dx (w g) (ijk - fx)^T   (src/nclr.h:206,223)
+    // x/y components ride in one packed fp32x2 register pair (FFMA2), z (3D) is scalar.
     const int n1 = P.n1;
-    const float four_inv_dx = 4.0f * P.inv_dx;
+    float2 v01 = make_float2(0.0f, 0.0f), B01[D];
+    float v2 = 0.0f, B2[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) B01[c] = make_float2(0.0f, 0.0f), B2[c] = 0.0f;
+    const float2 plus1 = make_float2(1.0f, 1.0f), minus1 = make_float2(-1.0f, -1.0f);
 #pragma unroll
     for (int ii = 0; ii < 3; ++ii)
 #pragma unroll
@@ -250,33 +253,49 @@ __global__ void __launch_bounds__(128) k_g2p_gather(ParticleStore S, uint32_t n,
                     const size_t node = ((size_t) (base[0] + ii) * n1 + (base[1] + jj)) * n1 + (base[2] + kk);
                     const float4 g = ldg4(grid + node);
                     const float weight = w[0][ii] * w[1][jj] * w[2][kk];
-                    const float dpos[3] = {(float) ii - fx[0], (float) jj - fx[1], (float) kk - fx[2]};
-                    const float gv[3] = {g.x, g.y, g.z};
+                    const float2 wv01 = __fmul2_rn(make_float2(weight, weight), make_float2(g.x, g.y));
+                    const float wv2 = weight * g.z;
+                    v01 = __fadd2_rn(v01, wv01);
+                    v2 += wv2;
+                    const int o[3] = {ii - 1, jj - 1, kk - 1};
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        const float wv = weight * gv[r];
-                        vn[r] += wv;
-                        const float t = four_inv_dx * wv;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) Cn(r, c) = fmaf(t, dpos[c], Cn(r, c));
+                    for (int c = 0; c < 3; ++c) {
+                        if (o[c] == 1) {
+                            B01[c] = __ffma2_rn(wv01, plus1, B01[c]);
+                            B2[c] += wv2;
+                        } else if (o[c] == -1) {
+                            B01[c] = __ffma2_rn(wv01, minus1, B01[c]);
+                            B2[c] -= wv2;
+                        }
                     }
                 }
             } else {
                 const size_t node = (size_t) (base[0] + ii) * n1 + (base[1] + jj);
                 const float4 g = ldg4(grid + node);
                 const float weight = w[0][ii] * w[1][jj];
-                const float dpos[2] = {(float) ii - fx[0], (float) jj - fx[1]};
-                const float gv[2] = {g.x, g.y};
+                const float2 wv01 = __fmul2_rn(make_float2(weight, weight), make_float2(g.x, g.y));
+                v01 = __fadd2_rn(v01, wv01);
+                const int o[2] = {ii - 1, jj - 1};
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const float wv = weight * gv[r];
-                    vn[r] += wv;
-                    const float t = four_inv_dx * wv;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) Cn(r, c) = fmaf(t, dpos[c], Cn(r, c));
+                for (int c = 0; c < 2; ++c) {
+                    if (o[c] == 1) B01[c] = __ffma2_rn(wv01, plus1, B01[c]);
+                    else if (o[c] == -1)
+                        B01[c] = __ffma2_rn(wv01, minus1, B01[c]);
                 }
             }
         }
+    float vn[D];
+    Mat<D> Cn;
+    vn[0] = v01.x, vn[1] = v01.y;
+    if constexpr (D == 3) vn[2] = v2;
+    const float four_inv_dx = 4.0f * P.inv_dx;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        const float fc = fx[c] - 1.0f;
+        Cn(0, c) = four_inv_dx * fmaf(-vn[0], fc, B01[c].x);
+        Cn(1, c) = four_inv_dx * fmaf(-vn[1], fc, B01[c].y);
+        if constexpr (D == 3) Cn(2, c) = four_inv_dx * fmaf(-vn[2], fc, B2[c]);
+    }
     g2p_update<D, MODEL>(p, Cn, vn, P);
     store_state<D>(S, i, p);
 }

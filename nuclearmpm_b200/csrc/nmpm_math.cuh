@@ -69,41 +69,72 @@ __device__ __forceinline__ float clampf(float v, float lo, float hi) { return (v
         (yv) = fmaf(-(s), _x, (c) * _y);   \
     }
 
+// ~1 ulp reciprocal / reciprocal square root: MUFU approximation + one Newton-Raphson step, no
+// slow-path branch (IEEE div/sqrt cost ~10 instructions each plus an FCHK branch, and the Jacobi
+// rotation parameters are one long dependent chain of them).
+__device__ __forceinline__ float rcp_nr(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+__device__ __forceinline__ float rsqrt_nr(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    const float h = 0.5f * y;
+    return fmaf(h, fmaf(-x * y, y, 1.0f), y);  // y + 0.5 y (1 - x y^2)
+}
+
 // One two-sided Jacobi step on the (p,q) 2x2 block of W, accumulating U and V — the body of
 // Eigen::JacobiSVD::compute's inner loop with internal::real_2x2_jacobi_svd and
 // JacobiRotation::makeJacobi inlined (restated in oracle/eigen_standin/Eigen/Dense).
+//
+// The rotation parameters are the same closed forms written without quotients of quotients:
+//   rot1 (symmetrising rotation, u = t/d):  s1 = 1/sqrt(1+u^2) = |d| h,  c1 = u/sqrt(1+u^2) = sgn(d) t h,
+//        h = rsqrt(t^2 + d^2)
+//   makeJacobi (tau = (x-z)/(2|y|), t = 1/(tau +- sqrt(tau^2+1))):
+//        t = sgn * deno / (|x-z| + sqrt((x-z)^2 + deno^2)),  deno = 2|y|,  sgn = +1 if x-z > 0 else -1
+//        c = rsqrt(t^2+1),  s = -sgn(y) t c
 template <int N, int P, int Q>
 __device__ __forceinline__ void jacobi_pq(Mat<N>& W, Mat<N>& U, Mat<N>& V, float& maxDiag, bool& finished) {
     const float thr = fmaxf(FLT_MIN, (2.0f * FLT_EPSILON) * maxDiag);
     if (fabsf(W(P, Q)) > thr || fabsf(W(Q, P)) > thr) {
         finished = false;
         float m00 = W(P, P), m01 = W(P, Q), m10 = W(Q, P), m11 = W(Q, Q);
-        float c1, s1;
+        float c1 = 1.0f, s1 = 0.0f;
         const float t = m00 + m11;
         const float d = m10 - m01;
-        if (fabsf(d) < FLT_MIN) {
-            s1 = 0.0f;
-            c1 = 1.0f;
-        } else {
-            const float u = t / d;
-            const float tmp = sqrtf(fmaf(u, u, 1.0f));
-            s1 = 1.0f / tmp;
-            c1 = u / tmp;
+        if (fabsf(d) >= FLT_MIN) {
+            const float r2 = fmaf(t, t, d * d);
+            if (r2 > 1e-30f) {
+                const float h = rsqrt_nr(r2);
+                s1 = fabsf(d) * h;
+                c1 = copysignf(t * h, t * d);
+            } else {  // both tiny: the textbook form is safe from underflow of the squares
+                const float u = t / d;
+                const float tmp = sqrtf(fmaf(u, u, 1.0f));
+                s1 = 1.0f / tmp;
+                c1 = u / tmp;
+            }
         }
         NMPM_ROT(m00, m10, c1, s1);
         NMPM_ROT(m01, m11, c1, s1);
         // makeJacobi(x = m00, y = m01, z = m11)
-        float cr, sr;
+        float cr = 1.0f, sr = 0.0f;
         const float deno = 2.0f * fabsf(m01);
-        if (deno < FLT_MIN) {
-            cr = 1.0f;
-            sr = 0.0f;
-        } else {
-            const float tau = (m00 - m11) / deno;
-            const float w = sqrtf(fmaf(tau, tau, 1.0f));
-            const float tt = 1.0f / ((tau > 0.0f) ? (tau + w) : (tau - w));
-            const float nn = 1.0f / sqrtf(fmaf(tt, tt, 1.0f));
-            // s = -sign(t) * (y/|y|) * |t| * n  ==  -(y/|y|) * t * n
+        if (deno >= FLT_MIN) {
+            const float xz = m00 - m11;
+            const float q2 = fmaf(xz, xz, deno * deno);
+            float tt;
+            if (q2 > 1e-30f) {
+                const float root = q2 * rsqrt_nr(q2);
+                tt = deno * rcp_nr(fabsf(xz) + root);
+                tt = (xz > 0.0f) ? tt : -tt;
+            } else {
+                const float tau = xz / deno;
+                const float w = sqrtf(fmaf(tau, tau, 1.0f));
+                tt = 1.0f / ((tau > 0.0f) ? (tau + w) : (tau - w));
+            }
+            const float nn = rsqrt_nr(fmaf(tt, tt, 1.0f));
             sr = -copysignf(1.0f, m01) * tt * nn;
             cr = nn;
         }
@@ -122,9 +153,6 @@ __device__ __forceinline__ void jacobi_pq(Mat<N>& W, Mat<N>& U, Mat<N>& V, float
     }
 }
 
-template <int N>
-__device__ __forceinline__ void swap_cols(Mat<N>& a, int i, int j);
-
 #define NMPM_SWAPF(a, b) \
     {                    \
         float _t = (a);  \
@@ -141,8 +169,9 @@ __device__ __forceinline__ void jacobi_svd(const Mat<N>& a, Mat<N>& U, float (&s
     for (int k = 1; k < N * N; ++k) scale = fmaxf(scale, fabsf(a.m[k]));
     if (scale == 0.0f) scale = 1.0f;
     Mat<N> W;
+    const float inv_scale = 1.0f / scale;  // one IEEE divide; W = a * (1/scale) is within 1 ulp of a / scale
 #pragma unroll
-    for (int k = 0; k < N * N; ++k) W.m[k] = a.m[k] / scale;
+    for (int k = 0; k < N * N; ++k) W.m[k] = a.m[k] * inv_scale;
 #pragma unroll
     for (int j = 0; j < N; ++j)
 #pragma unroll

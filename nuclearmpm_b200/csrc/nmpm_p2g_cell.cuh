@@ -4,19 +4,21 @@
 // 313-337 — there a serial loop doing 3^dim read-modify-writes per particle.  Here:
 //
 //   phase A (lane = particle): each warp takes 32 consecutive slots of the cell-sorted store, loads
-//     them with coalesced float4 reads, runs polar/SVD + stress in registers and leaves a 16-word
-//     packet {fx, mass, mass*v, affine} + the linear index of the stencil's base node in shared memory.
-//   phase B (lane = stencil node, 27 of 32 lanes in 3D): the warp walks its 32 packets in slot order;
-//     every lane evaluates ITS node's weight and fused momentum (packet reads are shared-memory
-//     broadcasts) and accumulates in registers.  Consecutive particles of the same cell form a
-//     segment; at a segment boundary each lane issues ONE vector reduction
-//     (RED.E.ADD.F32x4 {px,py,pz,m}) for its node.
+//     them with coalesced float4 reads, runs polar/SVD + stress in registers and leaves a folded
+//     packet in shared memory:
+//         b  = mass*v - dx * A*fx        (so that  mass*v + A*((ijk-fx)*dx) = b + (dx*A)*ijk )
+//         A' = dx * A,  mass,  the 3x3 per-axis weights,  linear index of the stencil's base node
+//   phase B (lane = stencil node, 27 of 32 lanes in 3D, 9 in 2D): the warp walks its packets in slot
+//     order TWO PARTICLES AT A TIME with packed fp32x2 math (FFMA2/FMUL2, sm_100+): packets of
+//     particles 2t and 2t+1 are interleaved in shared memory so one LDS.128 broadcast yields two
+//     values for both particles as register pairs.  Every lane evaluates ITS node's weight and fused
+//     momentum and accumulates in registers (even/odd particle sums in the two halves).  Consecutive
+//     particles of the same cell form a segment; at a segment boundary each lane issues ONE vector
+//     reduction (RED.E.ADD.F32x4 {px,py,pz,m}) for its node.
 //
 // Global atomics per particle drop from 3^dim*(dim+1) scalar (or 3^dim vector) to 3^dim/ppc vector
 // reductions (ppc = particles per cell; 3.4 at 8 ppc in 3D), and no shared-memory float atomics are
 // used at all — on sm_100a those are CAS loops (ATOMS.CAST.SPIN), see DESIGN.md.
-// Weights are evaluated per lane as fma(t*t, k_i, b_i) with t = fx - c_i, which is bit-identical to
-// the reference's three formulas (src/nclr.h:124-127).
 #pragma once
 #include "nmpm_kernels.cuh"
 
@@ -24,13 +26,27 @@ namespace nmpm {
 
 constexpr int kP2GWarps = 4;
 
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+
+template <int D>
+struct P2GPacket {
+    // values per particle that phase B consumes through packed loads: b (D), A' (D*D), mass
+    static constexpr int NV = D + D * D + 1;          // 13 (3D) / 7 (2D)
+    static constexpr int NQ4 = (NV + 1) / 2;          // float4 words per particle PAIR: 7 / 4
+    static constexpr int WSTRIDE = 34;                // padded row stride of the weight table (bank spread)
+};
+
 template <int D, int MODEL>
 __global__ void __launch_bounds__(kP2GWarps * 32) k_p2g_cell(ParticleStore S, uint32_t n, MaterialParams P,
                                                              float4* __restrict__ grid, int* __restrict__ error_flag) {
+    using PK = P2GPacket<D>;
     constexpr int NODES = (D == 3) ? 27 : 9;
-    constexpr int NPK = (D == 3) ? 4 : 3;  // float4 words per packet
-    __shared__ float4 pk[kP2GWarps][NPK][32];
-    __shared__ int node0[kP2GWarps][32];
+    // pk[warp][q][t] = { val_{2q}(2t), val_{2q}(2t+1), val_{2q+1}(2t), val_{2q+1}(2t+1) }
+    __shared__ float4 pk[kP2GWarps][PK::NQ4][16];
+    __shared__ __align__(8) float wt[kP2GWarps][D * 3][PK::WSTRIDE];  // wt[d*3+i][slot]
+    __shared__ __align__(8) int node0[kP2GWarps][32];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t first = (blockIdx.x * kP2GWarps + warp) * 32u;
@@ -39,25 +55,44 @@ __global__ void __launch_bounds__(kP2GWarps * 32) k_p2g_cell(ParticleStore S, ui
     const int n1 = P.n1;
 
     // ---- phase A ---------------------------------------------------------------------------
-    if (lane < cnt) {
-        PState<D> p;
-        load_for_p2g<D>(S, first + lane, p);
-        int base[D];
-        float fx[D], w[D][3];
-        if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
-        const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, p.mass, p.volume, P);
-        if constexpr (D == 3) {
-            pk[warp][0][lane] = make_float4(fx[0], fx[1], fx[2], p.mass);
-            pk[warp][1][lane] = make_float4(p.v[0] * p.mass, p.v[1] * p.mass, p.v[2] * p.mass, A.m[0]);
-            pk[warp][2][lane] = make_float4(A.m[1], A.m[2], A.m[3], A.m[4]);
-            pk[warp][3][lane] = make_float4(A.m[5], A.m[6], A.m[7], A.m[8]);
-            node0[warp][lane] = (base[0] * n1 + base[1]) * n1 + base[2];
-        } else {
-            pk[warp][0][lane] = make_float4(fx[0], fx[1], p.mass, 0.0f);
-            pk[warp][1][lane] = make_float4(p.v[0] * p.mass, p.v[1] * p.mass, 0.0f, 0.0f);
-            pk[warp][2][lane] = make_float4(A.m[0], A.m[1], A.m[2], A.m[3]);
-            node0[warp][lane] = base[0] * n1 + base[1];
+    {
+        float vals[PK::NV + 1];
+        float w[D][3];
+        int nd = -1;
+#pragma unroll
+        for (int k = 0; k <= PK::NV; ++k) vals[k] = 0.0f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) w[d][0] = w[d][1] = w[d][2] = 0.0f;
+        if (lane < cnt) {
+            PState<D> p;
+            load_for_p2g<D>(S, first + lane, p);
+            int base[D];
+            float fx[D];
+            if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
+            const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, p.mass, p.volume, P);
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                float afx = A(r, 0) * fx[0];
+#pragma unroll
+                for (int k = 1; k < D; ++k) afx = fmaf(A(r, k), fx[k], afx);
+                vals[r] = fmaf(-P.dx, afx, p.v[r] * p.mass);  // b_r
+#pragma unroll
+                for (int c = 0; c < D; ++c) vals[D + r * D + c] = P.dx * A(r, c);  // A'_rc (row-major here)
+            }
+            vals[D + D * D] = p.mass;
+            nd = base[0] * n1 + base[1];
+            if constexpr (D == 3) nd = nd * n1 + base[2];
         }
+        float* pkf = reinterpret_cast<float*>(&pk[warp][0][0]);
+        const int t = lane >> 1, h = lane & 1;
+#pragma unroll
+        for (int k = 0; k < PK::NV; ++k) pkf[((k >> 1) * 16 + t) * 4 + (k & 1) * 2 + h] = vals[k];
+        if constexpr (PK::NV & 1) pkf[((PK::NV >> 1) * 16 + t) * 4 + 2 + h] = 0.0f;
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) wt[warp][d * 3 + i][lane] = w[d][i];
+        node0[warp][lane] = nd;
     }
     __syncwarp();
 
@@ -69,63 +104,80 @@ __global__ void __launch_bounds__(kP2GWarps * 32) k_p2g_cell(ParticleStore S, ui
     } else {
         ijk[0] = lane / 3, ijk[1] = lane % 3;
     }
-    float fi[D], ci[D], ki[D], bi[D];
+    float2 fi[D];
     int lane_off = 0;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-        fi[d] = (float) ijk[d];
-        ci[d] = 1.5f - 0.5f * fi[d];                // 1.5, 1.0, 0.5
-        ki[d] = (ijk[d] == 1) ? -1.0f : 0.5f;       // w1 = 0.75 - t^2 ; w0,w2 = 0.5 t^2
-        bi[d] = (ijk[d] == 1) ? 0.75f : 0.0f;
+        fi[d] = splat2((float) ijk[d]);
         lane_off = lane_off * n1 + ijk[d];
     }
-
-    float acc[D], acc_m = 0.0f;
+    const float* wrow[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) acc[d] = 0.0f;
+    for (int d = 0; d < D; ++d) wrow[d] = &wt[warp][d * 3 + ijk[d]][0];
+
+    float2 acc[D], acc_m = splat2(0.0f);
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = splat2(0.0f);
     int cur = node0[warp][0];
 
-    for (int j = 0; j < cnt; ++j) {
-        const int nj = node0[warp][j];
-        if (nj != cur) {  // warp-uniform: segment boundary
-            red_add_f32x4(grid + (size_t) (cur + lane_off), node_pack<D>(acc, acc_m));
+    auto flush = [&](int node) {
+        float mom[D];
 #pragma unroll
-            for (int d = 0; d < D; ++d) acc[d] = 0.0f;
-            acc_m = 0.0f;
-            cur = nj;
-        }
-        float fx[D], mv[D], mass;
-        Mat<D> A;
-        if constexpr (D == 3) {
-            const float4 a = pk[warp][0][j], b = pk[warp][1][j], c = pk[warp][2][j], e = pk[warp][3][j];
-            fx[0] = a.x, fx[1] = a.y, fx[2] = a.z, mass = a.w;
-            mv[0] = b.x, mv[1] = b.y, mv[2] = b.z;
-            A.m[0] = b.w, A.m[1] = c.x, A.m[2] = c.y, A.m[3] = c.z, A.m[4] = c.w;
-            A.m[5] = e.x, A.m[6] = e.y, A.m[7] = e.z, A.m[8] = e.w;
-        } else {
-            const float4 a = pk[warp][0][j], b = pk[warp][1][j], c = pk[warp][2][j];
-            fx[0] = a.x, fx[1] = a.y, mass = a.z;
-            mv[0] = b.x, mv[1] = b.y;
-            A.m[0] = c.x, A.m[1] = c.y, A.m[2] = c.z, A.m[3] = c.w;
-        }
-        float weight = 1.0f, dpos[D];
+        for (int d = 0; d < D; ++d) mom[d] = acc[d].x + acc[d].y;
+        red_add_f32x4(grid + (size_t) (node + lane_off), node_pack<D>(mom, acc_m.x + acc_m.y));
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const float t = fx[d] - ci[d];
-            const float wd = fmaf(t * t, ki[d], bi[d]);
-            weight = (d == 0) ? wd : weight * wd;
-            dpos[d] = (fi[d] - fx[d]) * P.dx;
+        for (int d = 0; d < D; ++d) acc[d] = splat2(0.0f);
+        acc_m = splat2(0.0f);
+    };
+
+    const int npairs = (cnt + 1) >> 1;
+    for (int t = 0; t < npairs; ++t) {
+        const int2 nn = *reinterpret_cast<const int2*>(&node0[warp][2 * t]);
+        // packed values for the pair (2t, 2t+1)
+        float2 val[PK::NV + 1];
+#pragma unroll
+        for (int q = 0; q < PK::NQ4; ++q) {
+            const float4 f = pk[warp][q][t];
+            val[2 * q] = make_float2(f.x, f.y);
+            val[2 * q + 1] = make_float2(f.z, f.w);
         }
+        float2 weight = *reinterpret_cast<const float2*>(wrow[0] + 2 * t);
+#pragma unroll
+        for (int d = 1; d < D; ++d) weight = fmul2(weight, *reinterpret_cast<const float2*>(wrow[d] + 2 * t));
+        // q_r = b_r + A'_r . ijk ; contribution = weight * q_r
+        float2 q[D];
 #pragma unroll
         for (int r = 0; r < D; ++r) {
-            float ad = A(r, 0) * dpos[0];
+            q[r] = val[r];
 #pragma unroll
-            for (int k = 1; k < D; ++k) ad = fmaf(A(r, k), dpos[k], ad);
-            acc[r] = fmaf(weight, mv[r] + ad, acc[r]);
+            for (int c = 0; c < D; ++c) q[r] = ffma2(val[D + r * D + c], fi[c], q[r]);
         }
-        acc_m = fmaf(weight, mass, acc_m);
+        const float2 mass = val[D + D * D];
+        const int nb = (nn.y < 0) ? nn.x : nn.y;  // odd tail: the padding slot has zero weight
+        if (nn.x == cur && nb == cur) {           // warp-uniform: both particles continue the segment
+#pragma unroll
+            for (int r = 0; r < D; ++r) acc[r] = ffma2(weight, q[r], acc[r]);
+            acc_m = ffma2(weight, mass, acc_m);
+        } else {
+            if (nn.x != cur) {
+                flush(cur);
+                cur = nn.x;
+            }
+            const float2 wa = make_float2(weight.x, 0.0f);
+#pragma unroll
+            for (int r = 0; r < D; ++r) acc[r] = ffma2(wa, q[r], acc[r]);
+            acc_m = ffma2(wa, mass, acc_m);
+            if (nb != cur) {
+                flush(cur);
+                cur = nb;
+            }
+            const float2 wb = make_float2(0.0f, weight.y);
+#pragma unroll
+            for (int r = 0; r < D; ++r) acc[r] = ffma2(wb, q[r], acc[r]);
+            acc_m = ffma2(wb, mass, acc_m);
+        }
     }
-    red_add_f32x4(grid + (size_t) (cur + lane_off), node_pack<D>(acc, acc_m));
+    flush(cur);
 }
 
 template <int D, int MODEL>

@@ -49,7 +49,9 @@ class Options(ct.Structure):
 
 
 def lib_path() -> Path:
-    return _PKG / "lib" / "libnmpm.so"
+    import os
+    override = os.environ.get("NMPM_LIB")  # experiments only: an alternative build of the SAME C-ABI
+    return Path(override) if override else _PKG / "lib" / "libnmpm.so"
 
 
 _lib = None
