@@ -5,6 +5,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -49,6 +50,8 @@ struct nmpm_sim {
 
     SortWorkspace sort;
     int tiles_per_axis = 0, key_bits = 0;
+    bool keys_valid = false;        // sort.keys_a holds the cell keys of store[cur] (written by the last G2P)
+    const uint32_t* perm = nullptr; // this step's sorted permutation (slot of the i-th sorted particle), or null
 
     int* d_error = nullptr;
     int* h_error = nullptr;  // pinned
@@ -60,6 +63,16 @@ struct nmpm_sim {
     long long steps_done = 0;
     long long launches = 0;
     int phase_next = 0;
+
+    // CUDA-graph cache: one captured step per host-side step state (store parity, sort phase, keys_valid)
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        int cur_after = 0;
+        bool keys_valid_after = false;
+        int launches = 0;
+    };
+    std::unordered_map<int, StepGraph> graphs;
+    bool graphs_ok = true;
 
     bool timing = false;
     cudaEvent_t ev[6]{};
@@ -278,6 +291,8 @@ void nmpm_destroy(nmpm_handle h) {
     cudaFree(h->sort.done_counter);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& kv : h->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -411,18 +426,22 @@ void* nmpm_get_stream(nmpm_handle h) { return h ? (void*) h->stream : nullptr; }
 // ---------------------------------------------------------------------------------------------
 // the step
 // ---------------------------------------------------------------------------------------------
+// K0: (keys from the previous G2P, or a key pass) + radix sort.  The reorder itself is fused into the
+// readers: P2G and G2P index the store through h->perm, and G2P writes the other store in sorted order.
 static int do_sort(nmpm_sim* h) {
+    h->perm = nullptr;
     if (h->n == 0) return NMPM_OK;
     const uint32_t n = (uint32_t) h->n;
     ParticleStore& S = h->store[h->cur];
-    NMPM_DISPATCH_DIM(h, (k_cell_keys<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(
-                             S, n, h->P, h->tiles_per_axis, h->sort.keys_a, nullptr, h->d_error)));
+    if (!h->keys_valid) {
+        NMPM_DISPATCH_DIM(h, (k_cell_keys<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(
+                                 S, n, h->P, h->tiles_per_axis, h->sort.keys_a, nullptr, h->d_error)));
+        h->launches++;
+    }
     uint32_t *ks = nullptr, *perm = nullptr;
-    h->launches += 1 + radix_sort_pairs(h->sort, n, h->key_bits, h->stream, &ks, &perm);
-    ParticleStore& T = h->store[h->cur ^ 1];
-    NMPM_DISPATCH_DIM(h, (k_reorder<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(S, T, perm, n)));
-    h->launches++;
-    h->cur ^= 1;
+    h->launches += radix_sort_pairs(h->sort, n, h->key_bits, h->stream, &ks, &perm);
+    h->keys_valid = false;
+    h->perm = perm;
     return NMPM_OK;
 }
 
@@ -435,10 +454,10 @@ static int do_p2g(nmpm_sim* h) {
     int variant = h->opt.p2g_variant;
     if (variant == 0) variant = (h->opt.sort_every > 0) ? 2 : 1;
     if (variant == 2) {
-        NMPM_DISPATCH(h, (launch_p2g_cell<D, MODEL>(S, n, h->P, h->grid, h->d_error, h->stream)));
+        NMPM_DISPATCH(h, (launch_p2g_cell<D, MODEL>(S, h->perm, n, h->P, h->grid, h->d_error, h->stream)));
     } else {
-        NMPM_DISPATCH(h, (k_p2g_scatter<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, n, h->P, h->grid,
-                                                                                            h->d_error)));
+        NMPM_DISPATCH(h, (k_p2g_scatter<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, h->perm, n, h->P,
+                                                                                            h->grid, h->d_error)));
     }
     h->launches++;
     return NMPM_OK;
@@ -453,9 +472,17 @@ static int do_grid_op(nmpm_sim* h) {
 static int do_g2p(nmpm_sim* h) {
     if (h->n == 0) return NMPM_OK;
     const uint32_t n = (uint32_t) h->n;
-    NMPM_DISPATCH(h, (k_g2p_gather<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(h->store[h->cur], n, h->P,
-                                                                                       h->grid, h->d_error)));
+    ParticleStore& S = h->store[h->cur];
+    ParticleStore& T = h->perm ? h->store[h->cur ^ 1] : S;
+    // emit the next step's keys only if the next step sorts
+    const bool next_sorts = h->opt.sort_every > 0 && ((h->steps_done + 1) % h->opt.sort_every) == 0;
+    uint32_t* keys_out = next_sorts ? h->sort.keys_a : nullptr;
+    NMPM_DISPATCH(h, (k_g2p_gather<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(
+                         S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error)));
     h->launches++;
+    if (h->perm) h->cur ^= 1;
+    h->perm = nullptr;
+    h->keys_valid = next_sorts;
     return NMPM_OK;
 }
 
@@ -518,17 +545,68 @@ static int sync_and_check(nmpm_sim* h) {
 
 extern "C" {
 
+// One whole step.  With opt.use_graph the launch sequence of each distinct host-side step state is
+// captured once into a CUDA graph and replayed afterwards (one launch per step instead of ~12).
+static int step_once(nmpm_sim* h) {
+    const bool can_graph = h->opt.use_graph && h->graphs_ok && !h->timing && h->phase_next == 0 && h->n > 0;
+    if (!can_graph) {
+        for (int ph = h->phase_next; ph < 3; ++ph)
+            if (int rc = run_phase(h, ph)) return rc;
+        h->phase_next = 0;
+        return NMPM_OK;
+    }
+    const int se = h->opt.sort_every;
+    const int key = h->cur | (h->keys_valid ? 2 : 0) | ((se > 0 ? (int) (h->steps_done % se) : 0) << 2);
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            h->graphs_ok = false;  // e.g. the legacy default stream: fall back to plain launches
+            return step_once(h);
+        }
+        const long long l0 = h->launches, s0 = h->steps_done;
+        int rc = NMPM_OK;
+        for (int ph = 0; ph < 3 && rc == NMPM_OK; ++ph) rc = run_phase(h, ph);
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+        nmpm_sim::StepGraph sg;
+        if (rc == NMPM_OK && e == cudaSuccess && g) e = cudaGraphInstantiate(&sg.exec, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (rc != NMPM_OK || e != cudaSuccess || !sg.exec) {
+            cudaGetLastError();
+            h->graphs_ok = false;
+            h->last_error = "CUDA graph capture failed; falling back to plain launches";
+            // host-side state already advanced by the capture pass: undo and run the step for real
+            h->steps_done = s0;
+            h->launches = l0;
+            h->cur = key & 1;
+            h->keys_valid = (key & 2) != 0;
+            h->perm = nullptr;
+            return step_once(h);
+        }
+        sg.cur_after = h->cur;
+        sg.keys_valid_after = h->keys_valid;
+        sg.launches = (int) (h->launches - l0);
+        it = h->graphs.emplace(key, sg).first;
+        CUDA_TRY(h, cudaGraphLaunch(it->second.exec, h->stream));
+        return NMPM_OK;  // host state was advanced while capturing
+    }
+    CUDA_TRY(h, cudaGraphLaunch(it->second.exec, h->stream));
+    h->cur = it->second.cur_after;
+    h->keys_valid = it->second.keys_valid_after;
+    h->perm = nullptr;
+    h->grid_valid = true;
+    h->steps_done++;
+    h->launches += it->second.launches;
+    return NMPM_OK;
+}
+
 int nmpm_advance(nmpm_handle h, int nsteps) {
     if (!h || nsteps < 0) return NMPM_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (int rc = poll_error(h)) return rc;
-    for (int s = 0; s < nsteps; ++s) {
-        // finish a partially executed step first (mixed nmpm_phase / nmpm_advance use)
-        for (int ph = h->phase_next; ph < 3; ++ph) {
-            if (int rc = run_phase(h, ph)) return rc;
-        }
-        h->phase_next = 0;
-    }
+    for (int s = 0; s < nsteps; ++s)
+        if (int rc = step_once(h)) return rc;
     CUDA_TRY(h, cudaMemcpyAsync(h->h_error, h->d_error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     return NMPM_OK;
 }
@@ -675,6 +753,8 @@ int nmpm_upload_particles(nmpm_handle h, const float* x, const float* v, const f
     h->launches += 2;
     h->cur ^= 1;
     h->phase_next = 0;
+    h->keys_valid = false;
+    h->perm = nullptr;
     // the sort cadence restarts so that the next step re-bins the new state
     h->steps_done = 0;
     CUDA_TRY(h, cudaMemsetAsync(h->d_error, 0, sizeof(int), h->stream));
@@ -687,9 +767,14 @@ int nmpm_upload_particles(nmpm_handle h, const float* x, const float* v, const f
 int nmpm_sort_debug(nmpm_handle h, int32_t* base, uint32_t* keys_unsorted, uint32_t* keys_sorted, uint32_t* perm,
                     uint32_t* ids) {
     if (!h) return NMPM_ERR_INVALID;
+    if (h->phase_next != 0) {
+        h->last_error = "nmpm_sort_debug: not allowed in the middle of a step";
+        return NMPM_ERR_INVALID;
+    }
     CUDA_TRY(h, cudaSetDevice(h->device));
     const size_t n = h->n, D = (size_t) h->dim;
     if (n == 0) return NMPM_OK;
+    h->keys_valid = false;  // the sort below consumes the key buffer
     if (int rc = ensure_staging(h, n * D * sizeof(int32_t))) return rc;
     ParticleStore& S = h->store[h->cur];
     int32_t* dbase = (int32_t*) h->staging;

@@ -83,12 +83,13 @@ __device__ __forceinline__ bool stencil_of(const float (&x)[D], const MaterialPa
 
 // ---- K2 (variant 1): one thread per particle, 3^D vector reductions --------------------------
 template <int D, int MODEL>
-__global__ void __launch_bounds__(128) k_p2g_scatter(ParticleStore S, uint32_t n, MaterialParams P,
-                                                     float4* __restrict__ grid, int* __restrict__ error_flag) {
+__global__ void __launch_bounds__(128) k_p2g_scatter(ParticleStore S, const uint32_t* __restrict__ perm, uint32_t n,
+                                                     MaterialParams P, float4* __restrict__ grid,
+                                                     int* __restrict__ error_flag) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     PState<D> p;
-    load_for_p2g<D>(S, i, p);
+    load_for_p2g<D>(S, perm ? __ldg(perm + i) : i, p);
     int base[D];
     float fx[D], w[D][3];
     if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
@@ -222,13 +223,20 @@ __device__ __forceinline__ void g2p_update(PState<D>& p, const Mat<D>& Cn, const
     }
 }
 
+// `perm` (nullable) fuses the re-binning reorder into this kernel: thread i reads slot perm[i] of `S`
+// and writes slot i of `T` (T may equal S when perm is null), so after the kernel `T` is in cell-sorted
+// order without a separate gather pass.  `keys_out` (nullable) receives the NEXT step's cell key of
+// the advected particle, so the next step's sort starts without a key pass.
 template <int D, int MODEL>
-__global__ void __launch_bounds__(128) k_g2p_gather(ParticleStore S, uint32_t n, MaterialParams P,
-                                                    const float4* __restrict__ grid, int* __restrict__ error_flag) {
+__global__ void __launch_bounds__(128) k_g2p_gather(ParticleStore S, ParticleStore T, const uint32_t* __restrict__ perm,
+                                                    uint32_t n, MaterialParams P, const float4* __restrict__ grid,
+                                                    uint32_t* __restrict__ keys_out, int tiles_per_axis,
+                                                    int* __restrict__ error_flag) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const uint32_t src = perm ? __ldg(perm + i) : i;
     PState<D> p;
-    load_for_g2p<D>(S, i, p);
+    load_for_g2p<D>(S, src, p);
     int base[D];
     float fx[D], w[D][3];
     if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
@@ -297,7 +305,23 @@ __global__ void __launch_bounds__(128) k_g2p_gather(ParticleStore S, uint32_t n,
         if constexpr (D == 3) Cn(2, c) = four_inv_dx * fmaf(-vn[2], fc, B2[c]);
     }
     g2p_update<D, MODEL>(p, Cn, vn, P);
-    store_state<D>(S, i, p);
+    store_state<D>(T, i, p);
+    if (perm) {
+        T.mv[i] = __ldg(S.mv + src);
+        T.id[i] = __ldg(S.id + src);
+    }
+    if (keys_out) {
+        int b[D];
+        bool bad = false;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const Stencil1 s = stencil_axis(p.x[d], P.inv_dx, P.res);
+            b[d] = s.base;
+            bad = bad || !s.ok;
+        }
+        // an out-of-grid position is flagged by the next step's P2G/G2P (that is when the reference throws)
+        keys_out[i] = bad ? 0xFFFFFFFFu : cell_key<D>(b, tiles_per_axis);
+    }
 }
 
 // ---- K5: import / export between the interchange layouts and the device store ---------------

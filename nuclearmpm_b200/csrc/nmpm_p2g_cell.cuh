@@ -39,8 +39,9 @@ struct P2GPacket {
 };
 
 template <int D, int MODEL>
-__global__ void __launch_bounds__(kP2GWarps * 32) k_p2g_cell(ParticleStore S, uint32_t n, MaterialParams P,
-                                                             float4* __restrict__ grid, int* __restrict__ error_flag) {
+__global__ void __launch_bounds__(kP2GWarps * 32) k_p2g_cell(ParticleStore S, const uint32_t* __restrict__ perm,
+                                                             uint32_t n, MaterialParams P, float4* __restrict__ grid,
+                                                             int* __restrict__ error_flag) {
     using PK = P2GPacket<D>;
     constexpr int NODES = (D == 3) ? 27 : 9;
     // pk[warp][q][t] = { val_{2q}(2t), val_{2q}(2t+1), val_{2q+1}(2t), val_{2q+1}(2t+1) }
@@ -65,7 +66,8 @@ __global__ void __launch_bounds__(kP2GWarps * 32) k_p2g_cell(ParticleStore S, ui
         for (int d = 0; d < D; ++d) w[d][0] = w[d][1] = w[d][2] = 0.0f;
         if (lane < cnt) {
             PState<D> p;
-            load_for_p2g<D>(S, first + lane, p);
+            // `perm` (nullable): the store is read THROUGH the sorted permutation, no reorder pass
+            load_for_p2g<D>(S, perm ? __ldg(perm + first + lane) : first + lane, p);
             int base[D];
             float fx[D];
             if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
@@ -181,10 +183,10 @@ __global__ void __launch_bounds__(kP2GWarps * 32) k_p2g_cell(ParticleStore S, ui
 }
 
 template <int D, int MODEL>
-inline void launch_p2g_cell(const ParticleStore& S, uint32_t n, const MaterialParams& P, float4* grid, int* error_flag,
-                            cudaStream_t st) {
+inline void launch_p2g_cell(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
+                            float4* grid, int* error_flag, cudaStream_t st) {
     const unsigned blocks = (n + kP2GWarps * 32 - 1) / (kP2GWarps * 32);
-    k_p2g_cell<D, MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, n, P, grid, error_flag);
+    k_p2g_cell<D, MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag);
 }
 
 }  // namespace nmpm
