@@ -1,0 +1,52 @@
+"""CPU checks of the drop-in boundary: include/nclr.h compiles (alone, and under the reference's own
+solver.cpp when /root/reference is present), links against libnmpm.so, prints like Eigen, and fails
+loudly without a GPU (no CPU fallback)."""
+import shutil
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+LIBDIR = ROOT / "nuclearmpm_b200" / "lib"
+REF = Path("/root/reference")
+
+
+def _build(tmp_path, src, out, extra=()):
+    import nuclearmpm_b200 as nm
+    nm.load_library()
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}", *extra, str(src), "-o",
+           str(tmp_path / out), f"-L{LIBDIR}", "-lnmpm", f"-Wl,-rpath,{LIBDIR}"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return tmp_path / out
+
+
+def test_header_compiles_warning_free_and_links(tmp_path):
+    exe = _build(tmp_path, ROOT / "tests" / "cpp" / "dropin_main.cpp", "dropin_main")
+    assert exe.exists()
+
+
+def test_matrix_stream_format_matches_eigen_default(tmp_path):
+    exe = _build(tmp_path, ROOT / "tests" / "cpp" / "format_main.cpp", "format_main")
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    # Eigen IOFormat(): stream precision 6, ' ' between columns, '\n' between rows, every coefficient
+    # right-aligned to the widest one of the matrix
+    assert out == ("0.4\n0.6\n--\n1 0\n0 1\n--\n 1.5   -2\n   3 4.25\n--\n1 0 0\n0 1 0\n0 0 0\n--\n"
+                   "3846.15 5769.23\n--\n0.123457\n0.123457\n0.123457\n")
+
+
+@pytest.mark.skipif(not (REF / "src" / "solver.cpp").exists(), reason="reference tree not present (GPU box)")
+def test_reference_solver_cpp_compiles_unchanged_against_dropin_header(tmp_path):
+    """src/solver.cpp of the reference, byte for byte, with include/ shadowing the reference's src/."""
+    src = tmp_path / "solver.cpp"
+    shutil.copyfile(REF / "src" / "solver.cpp", src)
+    import nuclearmpm_b200 as nm
+    nm.load_library()
+    exe = tmp_path / "nuclear_mpm_solver_ref_source"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-w", f"-I{ROOT / 'include'}", f"-I{REF / 'flags' / 'include'}", str(src),
+                    "-o", str(exe), f"-L{LIBDIR}", "-lnmpm", f"-Wl,-rpath,{LIBDIR}"], check=True, capture_output=True)
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([str(exe), "--steps", "1", "--cubes", "1", "--cube0-x", "0.4", "--cube0-y", "0.6"],
+                           capture_output=True, text=True, cwd=tmp_path)
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr  # fails loudly, never computes on the host
