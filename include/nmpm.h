@@ -117,6 +117,8 @@ int nmpm_key_tile_bits(nmpm_handle h);
  * first_piola_kirchoff_stress — src/nclr.h:313-337).  count matrices, host pointers, column-major. */
 int nmpm_svd_batch(int dim, size_t count, const float *A, float *U, float *sig, float *V, int device);
 int nmpm_polar_batch(int dim, size_t count, const float *A, float *R, int device);
+/* snow plasticity projection U clamp(sig, lo, hi) V^T of nclr_svd(A) — src/nclr.h:239-247 */
+int nmpm_snow_project_batch(int dim, size_t count, const float *A, float lo, float hi, float *G, int device);
 int nmpm_affine_debug(nmpm_handle h, float *A_out /* n*dim*dim, input order */);
 
 /* Timing: accumulated CUDA-event milliseconds per phase since the last reset (only recorded when

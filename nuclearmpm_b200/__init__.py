@@ -6,7 +6,7 @@ include/nclr.h, the drop-in C++ header.  This package is the Python mirror of th
 There is no CPU fallback: importing works anywhere, computing needs a B200.
 """
 from .sim import (MPMSimulation, MaterialModel, NmpmError, OutOfGridError, cube, lib_path, load_library,  # noqa: F401
-                  polar_batch, svd_batch)
+                  polar_batch, snow_project_batch, svd_batch)
 
 __all__ = ["MPMSimulation", "MaterialModel", "NmpmError", "OutOfGridError", "cube", "lib_path", "load_library",
-           "svd_batch", "polar_batch"]
+           "svd_batch", "polar_batch", "snow_project_batch"]

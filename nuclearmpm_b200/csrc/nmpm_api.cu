@@ -812,7 +812,8 @@ int nmpm_affine_debug(nmpm_handle h, float* A_out) {
     return NMPM_OK;
 }
 
-static int svd_polar_batch(int dim, size_t count, const float* A, float* U, float* sig, float* V, float* R, int device) {
+static int svd_polar_batch(int dim, size_t count, const float* A, float* U, float* sig, float* V, float* R, int device,
+                           float* G = nullptr, float lo = 0.0f, float hi = 0.0f) {
     if ((dim != 2 && dim != 3) || (count && !A)) return NMPM_ERR_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -825,19 +826,21 @@ static int svd_polar_batch(int dim, size_t count, const float* A, float* U, floa
     CUDA_TRY(h, cudaSetDevice(device));
     const size_t w = count * (size_t) (dim * dim);
     float* d = nullptr;
-    CUDA_TRY(h, cudaMalloc(&d, 5 * w * sizeof(float)));
+    CUDA_TRY(h, cudaMalloc(&d, 6 * w * sizeof(float)));
     cudaError_t e = cudaMemcpy(d, A, w * sizeof(float), cudaMemcpyHostToDevice);
-    float *dU = U ? d + w : nullptr, *dS = d + 2 * w, *dV = d + 3 * w, *dR = R ? d + 4 * w : nullptr;
+    float *dU = U ? d + w : nullptr, *dS = d + 2 * w, *dV = d + 3 * w, *dR = R ? d + 4 * w : nullptr,
+          *dG = G ? d + 5 * w : nullptr;
     if (e == cudaSuccess) {
-        if (dim == 2) k_svd_batch<2><<<blocks_for(count, 128), 128>>>(d, count, dU, dS, dV, dR);
+        if (dim == 2) k_svd_batch<2><<<blocks_for(count, 128), 128>>>(d, count, dU, dS, dV, dR, dG, lo, hi);
         else
-            k_svd_batch<3><<<blocks_for(count, 128), 128>>>(d, count, dU, dS, dV, dR);
+            k_svd_batch<3><<<blocks_for(count, 128), 128>>>(d, count, dU, dS, dV, dR, dG, lo, hi);
         e = cudaDeviceSynchronize();
     }
     if (e == cudaSuccess && U) e = cudaMemcpy(U, dU, w * sizeof(float), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && sig) e = cudaMemcpy(sig, dS, w * sizeof(float), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && V) e = cudaMemcpy(V, dV, w * sizeof(float), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && R) e = cudaMemcpy(R, dR, w * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && G) e = cudaMemcpy(G, dG, w * sizeof(float), cudaMemcpyDeviceToHost);
     cudaFree(d);
     CUDA_TRY(h, e);
     return NMPM_OK;
@@ -850,6 +853,11 @@ int nmpm_svd_batch(int dim, size_t count, const float* A, float* U, float* sig, 
 int nmpm_polar_batch(int dim, size_t count, const float* A, float* R, int device) {
     if (!R) return NMPM_ERR_INVALID;
     return svd_polar_batch(dim, count, A, nullptr, nullptr, nullptr, R, device);
+}
+
+int nmpm_snow_project_batch(int dim, size_t count, const float* A, float lo, float hi, float* G, int device) {
+    if (!G) return NMPM_ERR_INVALID;
+    return svd_polar_batch(dim, count, A, nullptr, nullptr, nullptr, nullptr, device, G, lo, hi);
 }
 
 int nmpm_timing_enable(nmpm_handle h, int on) {

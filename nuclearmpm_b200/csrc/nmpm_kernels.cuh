@@ -195,31 +195,22 @@ __device__ __forceinline__ void g2p_update(PState<D>& p, const Mat<D>& Cn, const
     Mat<D> Fn = mat_mul<D>(M, p.F);
     if constexpr (MODEL == 1) {  // jelly (src/nclr.h:232-234)
         p.F = Fn;
-    } else {
-        Mat<D> U, V;
-        float sig[D];
-        nclr_svd<D>(Fn, U, sig, V);
-        if constexpr (MODEL == 0) {  // snow plasticity (src/nclr.h:239-250)
+    } else if constexpr (MODEL == 0) {  // snow plasticity (src/nclr.h:239-250)
+        const float old_J = det(Fn);
+        Fn = snow_project(Fn, 0.975f, 1.0045f);  // U clamp(sig) V^T
+        p.Jp = clampf(p.Jp * old_J / det(Fn), 0.6f, 20.0f);
+        p.F = Fn;
+    } else {  // liquid (src/nclr.h:252-258): F = diag<dim>(1) with F(0,0) = J = prod(sig)
+        // prod(sig) needs no SVD: in 3D the reference's sign fix makes det U = det V = +1, so
+        // sig0 sig1 sig2 = det(F'); in 2D the fix is a no-op (Q3), all sig >= 0, so sig0 sig1 = |det F'|.
+        // (The reference multiplies the float singular values in double, Q8; the difference to the
+        // fp32 determinant is a few ulp of |F'|^dim, far inside the F tolerance.)
+        float J = det(Fn);
+        if constexpr (D == 2) J = fabsf(J);
 #pragma unroll
-            for (int d = 0; d < D; ++d) sig[d] = clampf(sig[d], 0.975f, 1.0045f);
-            const float old_J = det(Fn);
-            Mat<D> Us;
-#pragma unroll
-            for (int j = 0; j < D; ++j)
-#pragma unroll
-                for (int i = 0; i < D; ++i) Us(i, j) = U(i, j) * sig[j];
-            Fn = mat_mul_bt<D>(Us, V);
-            p.Jp = clampf(p.Jp * old_J / det(Fn), 0.6f, 20.0f);
-            p.F = Fn;
-        } else {  // liquid (src/nclr.h:252-258): J in double, F = diag<dim>(1) with F(0,0) = J
-            double J = 1.0;
-#pragma unroll
-            for (int d = 0; d < D; ++d) J *= (double) sig[d];
-#pragma unroll
-            for (int k = 0; k < D * D; ++k) p.F.m[k] = 0.0f;
-            p.F(1, 1) = 1.0f;
-            p.F(0, 0) = (float) J;
-        }
+        for (int k = 0; k < D * D; ++k) p.F.m[k] = 0.0f;
+        p.F(1, 1) = 1.0f;
+        p.F(0, 0) = J;
     }
 }
 
@@ -435,7 +426,7 @@ __global__ void __launch_bounds__(256) k_export_grid(const float4* __restrict__ 
 // ---- unit hooks -------------------------------------------------------------------------------
 template <int D>
 __global__ void k_svd_batch(const float* __restrict__ A, size_t count, float* __restrict__ U, float* __restrict__ S,
-                            float* __restrict__ V, float* __restrict__ R) {
+                            float* __restrict__ V, float* __restrict__ R, float* __restrict__ G, float lo, float hi) {
     const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     Mat<D> a, u, v;
@@ -446,6 +437,11 @@ __global__ void k_svd_batch(const float* __restrict__ A, size_t count, float* __
         const Mat<D> r = nclr_polar_R(a);
 #pragma unroll
         for (int k = 0; k < D * D; ++k) R[i * D * D + k] = r.m[k];
+    }
+    if (G) {
+        const Mat<D> g = snow_project(a, lo, hi);
+#pragma unroll
+        for (int k = 0; k < D * D; ++k) G[i * D * D + k] = g.m[k];
     }
     if (U) {
         nclr_svd<D>(a, u, sig, v);

@@ -10,19 +10,29 @@
 //   hardening      src/nclr.h:351-372      (Q8: exp in double)
 #pragma once
 #include <cfloat>
+#include <cmath>
 #include <cuda_runtime.h>
+
+// The math below is device code.  It is ALSO compilable for the host (plain g++, see
+// tests/cpp/hostmath.cpp) so that the CPU test-suite can check the algorithms against the oracle
+// before any GPU time is spent; libnmpm.so never calls the host instantiations.
+#if defined(__CUDACC__)
+#define NMPM_HD __host__ __device__ __forceinline__
+#else
+#define NMPM_HD inline
+#endif
 
 namespace nmpm {
 
 template <int D>
 struct Mat {
     float m[D * D];  // column-major: (i,j) at i + j*D, like Eigen
-    __device__ __forceinline__ float& operator()(int i, int j) { return m[i + j * D]; }
-    __device__ __forceinline__ float operator()(int i, int j) const { return m[i + j * D]; }
+    NMPM_HD float& operator()(int i, int j) { return m[i + j * D]; }
+    NMPM_HD float operator()(int i, int j) const { return m[i + j * D]; }
 };
 
 template <int D>
-__device__ __forceinline__ Mat<D> mat_mul(const Mat<D>& a, const Mat<D>& b) {
+NMPM_HD Mat<D> mat_mul(const Mat<D>& a, const Mat<D>& b) {
     Mat<D> r;
 #pragma unroll
     for (int j = 0; j < D; ++j)
@@ -38,7 +48,7 @@ __device__ __forceinline__ Mat<D> mat_mul(const Mat<D>& a, const Mat<D>& b) {
 
 // a * b^T
 template <int D>
-__device__ __forceinline__ Mat<D> mat_mul_bt(const Mat<D>& a, const Mat<D>& b) {
+NMPM_HD Mat<D> mat_mul_bt(const Mat<D>& a, const Mat<D>& b) {
     Mat<D> r;
 #pragma unroll
     for (int j = 0; j < D; ++j)
@@ -52,14 +62,14 @@ __device__ __forceinline__ Mat<D> mat_mul_bt(const Mat<D>& a, const Mat<D>& b) {
     return r;
 }
 
-__device__ __forceinline__ float det(const Mat<2>& a) { return a(0, 0) * a(1, 1) - a(1, 0) * a(0, 1); }
+NMPM_HD float det(const Mat<2>& a) { return a(0, 0) * a(1, 1) - a(1, 0) * a(0, 1); }
 // cofactors along row 0, the order Eigen's fixed-size determinant uses
-__device__ __forceinline__ float det(const Mat<3>& a) {
+NMPM_HD float det(const Mat<3>& a) {
     return a(0, 0) * (a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1)) - a(0, 1) * (a(1, 0) * a(2, 2) - a(1, 2) * a(2, 0)) +
            a(0, 2) * (a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0));
 }
 
-__device__ __forceinline__ float clampf(float v, float lo, float hi) { return (v < lo) ? lo : (hi < v) ? hi : v; }
+NMPM_HD float clampf(float v, float lo, float hi) { return (v < lo) ? lo : (hi < v) ? hi : v; }
 
 // Plane rotation of two length-N "vectors" given as register arrays: x' = c x + s y ; y' = -s x + c y
 #define NMPM_ROT(xv, yv, c, s)             \
@@ -72,17 +82,51 @@ __device__ __forceinline__ float clampf(float v, float lo, float hi) { return (v
 // ~1 ulp reciprocal / reciprocal square root: MUFU approximation + one Newton-Raphson step, no
 // slow-path branch (IEEE div/sqrt cost ~10 instructions each plus an FCHK branch, and the Jacobi
 // rotation parameters are one long dependent chain of them).
-__device__ __forceinline__ float rcp_nr(float x) {
+// raw MUFU approximations (~2^-22 relative error); host builds use the exact value
+NMPM_HD float rcp_approx(float x) {
+#ifdef __CUDA_ARCH__
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return fmaf(r, fmaf(-x, r, 1.0f), r);
+    return r;
+#else
+    return 1.0f / x;
+#endif
 }
-__device__ __forceinline__ float rsqrt_nr(float x) {
+NMPM_HD float rsqrt_approx(float x) {
+#ifdef __CUDA_ARCH__
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+NMPM_HD float sqrt_approx(float x) {
+#ifdef __CUDA_ARCH__
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return sqrtf(x);
+#endif
+}
+NMPM_HD float rcp_nr(float x) {
+    const float r = rcp_approx(x);
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+NMPM_HD float rsqrt_nr(float x) {
+    const float y = rsqrt_approx(x);
     const float h = 0.5f * y;
     return fmaf(h, fmaf(-x * y, y, 1.0f), y);  // y + 0.5 y (1 - x y^2)
 }
+#ifndef __CUDA_ARCH__
+// host stand-ins for the round-to-nearest intrinsics (host test builds use -ffp-contract=off)
+inline float nmpm_fmul_rn(float a, float b) { return a * b; }
+inline float nmpm_fsub_rn(float a, float b) { return a - b; }
+#else
+__device__ __forceinline__ float nmpm_fmul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float nmpm_fsub_rn(float a, float b) { return __fsub_rn(a, b); }
+#endif
 
 // One two-sided Jacobi step on the (p,q) 2x2 block of W, accumulating U and V — the body of
 // Eigen::JacobiSVD::compute's inner loop with internal::real_2x2_jacobi_svd and
@@ -95,7 +139,7 @@ __device__ __forceinline__ float rsqrt_nr(float x) {
 //        t = sgn * deno / (|x-z| + sqrt((x-z)^2 + deno^2)),  deno = 2|y|,  sgn = +1 if x-z > 0 else -1
 //        c = rsqrt(t^2+1),  s = -sgn(y) t c
 template <int N, int P, int Q>
-__device__ __forceinline__ void jacobi_pq(Mat<N>& W, Mat<N>& U, Mat<N>& V, float& maxDiag, bool& finished) {
+NMPM_HD void jacobi_pq(Mat<N>& W, Mat<N>& U, Mat<N>& V, float& maxDiag, bool& finished) {
     const float thr = fmaxf(FLT_MIN, (2.0f * FLT_EPSILON) * maxDiag);
     if (fabsf(W(P, Q)) > thr || fabsf(W(Q, P)) > thr) {
         finished = false;
@@ -163,7 +207,7 @@ __device__ __forceinline__ void jacobi_pq(Mat<N>& W, Mat<N>& U, Mat<N>& V, float
 // Eigen::JacobiSVD<Matrix<float,N,N>>(a, ComputeFullU|ComputeFullV): a = U diag(sv) V^T,
 // sv >= 0 descending (first maximum wins ties, zero tail left in place).
 template <int N>
-__device__ __forceinline__ void jacobi_svd(const Mat<N>& a, Mat<N>& U, float (&sv)[N], Mat<N>& V) {
+NMPM_HD void jacobi_svd(const Mat<N>& a, Mat<N>& U, float (&sv)[N], Mat<N>& V) {
     float scale = fabsf(a.m[0]);
 #pragma unroll
     for (int k = 1; k < N * N; ++k) scale = fmaxf(scale, fabsf(a.m[k]));
@@ -256,7 +300,7 @@ __device__ __forceinline__ void jacobi_svd(const Mat<N>& a, Mat<N>& U, float (&s
 // nclr_svd<dim> (src/nclr_math.h:50-74): JacobiSVD, then force det U = det V = +1 by flipping
 // column 2 and sigma_2.  In 2D the reference's hard-coded index 2 is out of bounds: no-op (Q3).
 template <int D>
-__device__ __forceinline__ void nclr_svd(const Mat<D>& a, Mat<D>& U, float (&sig)[D], Mat<D>& V) {
+NMPM_HD void nclr_svd(const Mat<D>& a, Mat<D>& U, float (&sig)[D], Mat<D>& V) {
     jacobi_svd<D>(a, U, sig, V);
     if constexpr (D == 3) {
         if (det(U) < 0.0f) {
@@ -273,7 +317,7 @@ __device__ __forceinline__ void nclr_svd(const Mat<D>& a, Mat<D>& U, float (&sig
 }
 
 // nclr_polar<dim> (src/nclr_math.h:76-98): rotation factor only (S is unused by every caller).
-__device__ __forceinline__ Mat<2> nclr_polar_R(const Mat<2>& m) {
+NMPM_HD Mat<2> nclr_polar_R(const Mat<2>& m) {
     const float x = m(0, 0) + m(1, 1);
     const float y = m(1, 0) - m(0, 1);
     const float scale = 1.0f / sqrtf(fmaf(x, x, y * y));
@@ -285,11 +329,154 @@ __device__ __forceinline__ Mat<2> nclr_polar_R(const Mat<2>& m) {
     R(1, 1) = c;
     return R;
 }
-__device__ __forceinline__ Mat<3> nclr_polar_R(const Mat<3>& m) {
+// ---------------------------------------------------------------------------------------------
+// Fast 3x3 path: G = sum_i f(sigma_i) u_i v_i^T without forming U, sigma, V of the reference's
+// two-sided JacobiSVD (which costs ~900 instructions per matrix and dominated both particle kernels,
+// profiles/r01a_ncu_summary.md).
+//
+// One-sided (Hestenes) Jacobi: rotate pairs of COLUMNS of A until they are mutually orthogonal,
+// accumulating the same rotations in V.  Then A V = [sigma_i u_i], i.e. column i IS sigma_i u_i, and
+//     G = sum_i (f(sigma_i) / sigma_i) a_i v_i^T.
+// The column of the smallest singular value is completed by a cross product, which reproduces the
+// reference's det(U) = det(V) = +1 rule (src/nclr_math.h:63-71): V is a product of rotations
+// (det +1), u_k := u_i x u_j for the cyclic order (i,j,k) makes det U = +1, and the signed
+// sigma_k = u_k . a_k carries sign(det A) exactly like the reference's flipped sigma_2.  Exactly
+// rank-2 input (3D jelly: third column of F is 0 forever, Q1) and tiny sigma_k (3D snow: F' has an
+// O(dt C) third row) are therefore handled without dividing by sigma_k.
+// Returns false when the matrix has (numerical) rank < 2 or is not finite: the caller falls back to
+// the reference-shaped two-sided Jacobi above.
+//   MODE 0: f = 1              (polar rotation R = U V^T)
+//   MODE 1: f = clamp(., lo, hi)  (snow plasticity projection, src/nclr.h:239-247)
+#define NMPM_HESTENES_PAIR(P, Q)                                                                    \
+    {                                                                                               \
+        const float gam = fmaf(a[P][0], a[Q][0], fmaf(a[P][1], a[Q][1], a[P][2] * a[Q][2]));         \
+        if (gam * gam > kTol2 * (nrm[P] * nrm[Q])) {                                                \
+            rotated = true;                                                                         \
+            const float d = nrm[Q] - nrm[P], g2 = gam + gam;                                        \
+            const float r = sqrt_approx(fmaf(d, d, g2 * g2));                                       \
+            float t = g2 * rcp_approx(fabsf(d) + r);                                                \
+            t = (d < 0.0f) ? -t : t;                                                                \
+            const float c = rsqrt_nr(fmaf(t, t, 1.0f)), sn = c * t;                                 \
+            nrm[P] = fmaf(-t, gam, nrm[P]);                                                         \
+            nrm[Q] = fmaf(t, gam, nrm[Q]);                                                          \
+            _Pragma("unroll") for (int e = 0; e < 3; ++e) {                                         \
+                const float x = a[P][e], y = a[Q][e];                                               \
+                a[P][e] = fmaf(c, x, -sn * y);                                                      \
+                a[Q][e] = fmaf(sn, x, c * y);                                                       \
+                const float vx = v[P][e], vy = v[Q][e];                                             \
+                v[P][e] = fmaf(c, vx, -sn * vy);                                                    \
+                v[Q][e] = fmaf(sn, vx, c * vy);                                                     \
+            }                                                                                       \
+        }                                                                                           \
+    }
+
+template <int MODE>
+NMPM_HD bool svd3_recompose(const Mat<3>& A, float lo, float hi, Mat<3>& G) {
+    // |a_p . a_q| <= 4 eps |a_p| |a_q| counts as orthogonal
+    constexpr float kTol2 = (4.0f * FLT_EPSILON) * (4.0f * FLT_EPSILON);
+    float a[3][3], v[3][3], nrm[3];  // a[j] = column j of A V,  v[j] = column j of V
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            a[j][e] = A(e, j);
+            v[j][e] = (e == j) ? 1.0f : 0.0f;
+        }
+        nrm[j] = fmaf(a[j][0], a[j][0], fmaf(a[j][1], a[j][1], a[j][2] * a[j][2]));
+    }
+    bool rotated = true;
+    for (int sweep = 0; sweep < 8 && rotated; ++sweep) {
+        rotated = false;
+        NMPM_HESTENES_PAIR(0, 1)
+        NMPM_HESTENES_PAIR(0, 2)
+        NMPM_HESTENES_PAIR(1, 2)
+    }
+    // squared singular values from the final columns (the running values above only steer the sweeps)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) nrm[j] = fmaf(a[j][0], a[j][0], fmaf(a[j][1], a[j][1], a[j][2] * a[j][2]));
+    // k = column of the smallest singular value (the reference's sorted index 2); ties -> last
+    const int k = (nrm[0] < nrm[1]) ? ((nrm[0] < nrm[2]) ? 0 : 2) : ((nrm[1] < nrm[2]) ? 1 : 2);
+    const float big = fmaxf(nrm[0], fmaxf(nrm[1], nrm[2]));
+    const float mid = (k == 0) ? fminf(nrm[1], nrm[2]) : (k == 1) ? fminf(nrm[0], nrm[2]) : fminf(nrm[0], nrm[1]);
+    // rank >= 2 and finite (NaN fails every comparison); 1e-10 on the squares = 1e-5 on sigma_mid/sigma_max
+    if (!(mid > 1e-10f * big) || !(big < 3.0e38f)) return false;
+    float inv[3], u[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        inv[j] = rsqrt_nr(fmaxf(nrm[j], 1e-37f));
+#pragma unroll
+        for (int e = 0; e < 3; ++e) u[j][e] = a[j][e] * inv[j];
+    }
+    // u_k = u_i x u_j with (i,j,k) cyclic
+    float p[3], q[3];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        p[e] = (k == 0) ? u[1][e] : (k == 1) ? u[2][e] : u[0][e];
+        q[e] = (k == 0) ? u[2][e] : (k == 1) ? u[0][e] : u[1][e];
+    }
+    const float ck[3] = {fmaf(p[1], q[2], -p[2] * q[1]), fmaf(p[2], q[0], -p[0] * q[2]), fmaf(p[0], q[1], -p[1] * q[0])};
+    float f[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const bool is_k = (j == k);
+        float sg = nrm[j] * inv[j];  // sigma_j >= 0
+        if (is_k) {
+            sg = fmaf(ck[0], a[j][0], fmaf(ck[1], a[j][1], ck[2] * a[j][2]));  // signed: u_k . (sigma_k u_k)
+#pragma unroll
+            for (int e = 0; e < 3; ++e) u[j][e] = ck[e];
+        }
+        f[j] = (MODE == 0) ? 1.0f : clampf(sg, lo, hi);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float acc = (f[0] * u[0][r]) * v[0][c];
+            acc = fmaf(f[1] * u[1][r], v[1][c], acc);
+            acc = fmaf(f[2] * u[2][r], v[2][c], acc);
+            G(r, c) = acc;
+        }
+    return true;
+}
+
+// rotation factor of the polar decomposition through the reference-shaped SVD (always valid)
+NMPM_HD Mat<3> nclr_polar_R_jacobi(const Mat<3>& m) {
     Mat<3> U, V;
     float sig[3];
     nclr_svd<3>(m, U, sig, V);
     return mat_mul_bt<3>(U, V);
+}
+NMPM_HD Mat<3> nclr_polar_R(const Mat<3>& m) {
+    Mat<3> R;
+    if (svd3_recompose<0>(m, 0.0f, 0.0f, R)) return R;
+    return nclr_polar_R_jacobi(m);
+}
+// snow: U clamp(sigma, lo, hi) V^T of nclr_svd(m)  (src/nclr.h:239-247)
+NMPM_HD Mat<3> snow_project(const Mat<3>& m, float lo, float hi) {
+    Mat<3> G;
+    if (svd3_recompose<1>(m, lo, hi, G)) return G;
+    Mat<3> U, V;
+    float sig[3];
+    nclr_svd<3>(m, U, sig, V);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float sj = clampf(sig[j], lo, hi);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) U(i, j) *= sj;
+    }
+    return mat_mul_bt<3>(U, V);
+}
+NMPM_HD Mat<2> snow_project(const Mat<2>& m, float lo, float hi) {
+    Mat<2> U, V;
+    float sig[2];
+    nclr_svd<2>(m, U, sig, V);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float sj = clampf(sig[j], lo, hi);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) U(i, j) *= sj;
+    }
+    return mat_mul_bt<2>(U, V);
 }
 
 struct MaterialParams {
@@ -303,7 +490,7 @@ struct MaterialParams {
 
 // hardening (src/nclr.h:351-372): snow exp(10(1-Jp)) evaluated in double then narrowed (Q8)
 template <int MODEL>
-__device__ __forceinline__ float hardening_e(float Jp) {
+NMPM_HD float hardening_e(float Jp) {
     if constexpr (MODEL == 0) return (float) exp(10.0 * (1.0 - (double) Jp));
     if constexpr (MODEL == 1) return 0.3f;
     return 1.0f;
@@ -312,7 +499,7 @@ __device__ __forceinline__ float hardening_e(float Jp) {
 // first_piola_kirchoff_stress (src/nclr.h:313-337): returns -(dt*vol)*(Dinv*PF) + mass*C with
 // PF = 2mu(F-R)F^T + lambda(J-1)J * ones(D,D)   (Q2)
 template <int D, int MODEL>
-__device__ __forceinline__ Mat<D> affine_matrix(const Mat<D>& F, const Mat<D>& C, float Jp, float mass, float volume,
+NMPM_HD Mat<D> affine_matrix(const Mat<D>& F, const Mat<D>& C, float Jp, float mass, float volume,
                                                 const MaterialParams& P) {
     const float e = hardening_e<MODEL>(Jp);
     const float mu = P.mu_0 * e, lambda = P.lambda_0 * e;
@@ -338,17 +525,17 @@ struct Stencil1 {
     float w[3];
     bool ok;  // stencil nodes base..base+2 inside [0,res] and x finite
 };
-__device__ __forceinline__ Stencil1 stencil_axis(float x, float inv_dx, int res) {
+NMPM_HD Stencil1 stencil_axis(float x, float inv_dx, int res) {
     Stencil1 s;
     // __fmul_rn / __fsub_rn: no FMA contraction, so base and fx are bit-identical to the strict-FP
     // reference for any res, not only powers of two (Q10)
-    const float g = __fmul_rn(x, inv_dx);
-    const float t = __fsub_rn(g, 0.5f);
+    const float g = nmpm_fmul_rn(x, inv_dx);
+    const float t = nmpm_fsub_rn(g, 0.5f);
     s.base = (int) t;  // cast<int>: truncation toward zero (Q4)
     // base >= 0 && base+2 <= res, written on the float so that NaN / inf fail too.  (The reference
     // converts NaN to INT_MIN on x86 and throws from vector::at; CUDA's cvt would give 0.)
     s.ok = (t > -1.0f) && (t < (float) (res - 1));
-    s.fx = __fsub_rn(g, (float) s.base);
+    s.fx = nmpm_fsub_rn(g, (float) s.base);
     const float a = 1.5f - s.fx, b = s.fx - 1.0f, c = s.fx - 0.5f;
     s.w[0] = 0.5f * (a * a);
     s.w[1] = 0.75f - (b * b);

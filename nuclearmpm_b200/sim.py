@@ -93,6 +93,7 @@ def load_library():
     sig("nmpm_key_tile_bits", ci, [vp])
     sig("nmpm_svd_batch", ci, [ci, sz, _fp, _fp, _fp, _fp, ci])
     sig("nmpm_polar_batch", ci, [ci, sz, _fp, _fp, ci])
+    sig("nmpm_snow_project_batch", ci, [ci, sz, _fp, cf, cf, _fp, ci])
     sig("nmpm_affine_debug", ci, [vp, _fp])
     sig("nmpm_timing_enable", ci, [vp, ci])
     sig("nmpm_timing_read", ci, [vp, _fp, ct.POINTER(ci), ci])
@@ -308,3 +309,15 @@ def polar_batch(A: np.ndarray, device: int = 0) -> np.ndarray:
     if rc:
         raise NmpmError(f"nmpm_polar_batch failed ({rc}): {L.nmpm_last_error(None).decode()}")
     return R
+
+
+def snow_project_batch(A: np.ndarray, lo: float = 0.975, hi: float = 1.0045, device: int = 0) -> np.ndarray:
+    """Device U clamp(sig, lo, hi) V^T of nclr_svd(A) (src/nclr.h:239-247), column-major (k,dim,dim)."""
+    L = load_library()
+    A = _f32(A)
+    k, d, _ = A.shape
+    G = np.empty_like(A)
+    rc = L.nmpm_snow_project_batch(d, k, _p(A), lo, hi, _p(G), device)
+    if rc:
+        raise NmpmError(f"nmpm_snow_project_batch failed ({rc}): {L.nmpm_last_error(None).decode()}")
+    return G

@@ -322,3 +322,20 @@ def test_full_size_properties_config2(model):
         one.advance(1)
         assert (one.particles()["Jp"] == np.float32(0.6)).all()
     assert np.isfinite(after["x"]).all()
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["snow_F", "snow_Fprime_q1", "snow_Fprime_phys", "jelly_rank2", "liquid_diag",
+                                  "general", "step0", "scaled"])
+def test_device_fast_polar_and_snow_projection(name):
+    """The register fast path (one-sided Jacobi recompose, csrc/nmpm_math.cuh) against the oracle's
+    nclr_polar / nclr_svd + clamp in every regime the solver meets (tests/mathcases.py)."""
+    from mathcases import TOL, matrices, oracle_reference
+    A = matrices()[name]
+    R = nm.polar_batch(A)
+    G = nm.snow_project_batch(A, 0.975, 1.0045)
+    Ro, Go, well = oracle_reference(co, A)
+    assert np.isfinite(R).all() and np.isfinite(G).all()
+    if well.any():
+        assert np.abs(R - Ro)[well].max() <= TOL[name]
+        assert np.abs(G - Go)[well].max() <= TOL[name]
