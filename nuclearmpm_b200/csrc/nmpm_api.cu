@@ -212,6 +212,11 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
     if (h->opt.slab_x1 <= 0) h->opt.slab_x1 = res + 1;
     const size_t n1 = (size_t) res + 1;
     h->cells = (dim == 3) ? n1 * n1 * n1 : n1 * n1;
+    if (h->cells >= 0xFFFFFFFFull) {
+        g_create_error = "grid too large: (res+1)^dim must fit 32 bits";
+        delete h;
+        return NMPM_ERR_INVALID;
+    }
     h->tiles_per_axis = (int) ((n1 + (1 << kTileBits) - 1) >> kTileBits);
     {
         size_t tiles = 1;

@@ -135,6 +135,9 @@ __global__ void __launch_bounds__(256) k_grid_op(float4* __restrict__ grid, size
     const size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= cells) return;
     float4 g = grid[idx];
+    // untouched node (all zero): normalisation is skipped (mass == 0) and the sticky walls only act on
+    // non-zero velocities, so the node stays as it is — leave before any index arithmetic
+    if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && g.w == 0.0f) return;
     float vel[D];
     float m;
     if constexpr (D == 3) {
@@ -142,16 +145,22 @@ __global__ void __launch_bounds__(256) k_grid_op(float4* __restrict__ grid, size
     } else {
         vel[0] = g.x, vel[1] = g.y, m = g.z;
     }
-    const bool was_zero = (m == 0.0f);
     int c[D];
     const int n1 = P.n1;
-    if constexpr (D == 3) {
-        c[2] = (int) (idx % n1);
-        c[1] = (int) ((idx / n1) % n1);
-        c[0] = (int) (idx / ((size_t) n1 * n1));
-    } else {
-        c[1] = (int) (idx % n1);
-        c[0] = (int) (idx / n1);
+    {   // node coordinates, 32-bit arithmetic (cells < 2^32 is checked at creation)
+        uint32_t r = (uint32_t) idx;
+        const uint32_t un1 = (uint32_t) n1;
+        if constexpr (D == 3) {
+            const uint32_t q = r / un1;
+            c[2] = (int) (r - q * un1);
+            const uint32_t q2 = q / un1;
+            c[1] = (int) (q - q2 * un1);
+            c[0] = (int) q2;
+        } else {
+            const uint32_t q = r / un1;
+            c[1] = (int) (r - q * un1);
+            c[0] = (int) q;
+        }
     }
     if (m > 0.0f) {
 #pragma unroll
@@ -167,12 +176,6 @@ __global__ void __launch_bounds__(256) k_grid_op(float4* __restrict__ grid, size
             for (int e = 0; e < D; ++e) vel[e] = 0.0f;
             m = 0.0f;
         }
-    }
-    if (was_zero && m == 0.0f) {
-        bool all_zero = true;
-#pragma unroll
-        for (int d = 0; d < D; ++d) all_zero = all_zero && (vel[d] == 0.0f);
-        if (all_zero) return;  // untouched empty node: nothing to write back
     }
     grid[idx] = node_pack<D>(vel, m);
 }
