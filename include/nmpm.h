@@ -50,9 +50,10 @@ typedef struct nmpm_options {
     int sort_every;   /* re-bin + radix-sort particles by cell key every k steps (default 1; 0 = never) */
     int p2g_variant;  /* 0 = auto, 1 = per-particle float4 REDs, 2 = cell-segmented register accumulation */
     int use_graph;    /* capture the step into a CUDA graph and replay it (default 1) */
-    int slab_x0;      /* multi-GPU x-slab: first owned node plane (default 0) */
-    int slab_x1;      /* multi-GPU x-slab: one past the last owned node plane (default res+1) */
-    int reserved[10];
+    int slab_x0;      /* multi-GPU x-slab: this sim owns particles with slab_x0 <= base.x < slab_x1 */
+    int slab_x1;      /* 0 (default) = not a slab: the sim owns the whole domain */
+    int capacity;     /* slab mode: particle slots to allocate (>= n; room for migrants). 0 = n */
+    int reserved[9];
 } nmpm_options;
 
 void nmpm_default_options(nmpm_options *opt);
@@ -133,18 +134,49 @@ long long nmpm_launch_count(nmpm_handle h);
 int nmpm_set_stream(nmpm_handle h, void *cuda_stream);
 void *nmpm_get_stream(nmpm_handle h);
 
-/* Multi-GPU slab plumbing (one process per GPU; the exchange itself is done by the caller with
- * NCCL send/recv on these device buffers, on the sim's stream — SURVEY.md §8(e)). */
+/* ---- Multi-GPU x-slabs -------------------------------------------------------
+ * One process per GPU, one handle per slab (nmpm_options.slab_x0/x1/capacity).  Nothing in the
+ * reference corresponds to this (it is a single address space, src/nclr.h:100-101); the slab step is
+ * advance() (src/nclr.h:80-84) cut at the two points where neighbouring slabs must talk:
+ *
+ *   nmpm_slab_p2g        re-bin + sort the slab's particles, clear node planes [x0, x1+2), P2G
+ *   -- exchange A: both neighbours swap their partial sums of the two shared node planes
+ *      (nmpm_grid_plane_ptr to send, nmpm_grid_add_planes to add what was received) --
+ *   nmpm_slab_grid_g2p   grid_op on planes [x0, x1+2) (the shared planes are updated redundantly on
+ *                        both sides, bit-identically), G2P, and packing of the particles whose new
+ *                        base.x left [x0, x1) into caller-provided device buffers
+ *   -- exchange B: counts, then the migrant records, to the left / right neighbour --
+ *   nmpm_slab_unpack     append the received records; they are binned by the next nmpm_slab_p2g
+ *
+ * The transport is the caller's (nuclearmpm_b200/slab.py: torch.distributed, NCCL send/recv on the
+ * sim's stream).  All calls are asynchronous on the sim's stream.  A migrant record is the reference's
+ * Particle<dim> AoS record (src/nclr.h:20-48: x, v, F, C, Jp, mass, volume, c) with the global particle
+ * id in the colour word: 64 B in 2D, 112 B in 3D. */
+size_t nmpm_migrate_record_bytes(nmpm_handle h);
 /* device pointer to node plane `x_plane` of the grid (contiguous n1^(dim-1) float4 nodes) */
 void *nmpm_grid_plane_ptr(nmpm_handle h, int x_plane);
 size_t nmpm_grid_plane_bytes(nmpm_handle h);
 /* add `planes` received node planes (device buffer) into the grid starting at x_plane */
 int nmpm_grid_add_planes(nmpm_handle h, int x_plane, int planes, const void *device_src);
-/* After G2P: move particles whose base.x left [slab_x0, slab_x1) into the send buffers.
- * Returns counts; payload = 28 floats per particle (27 state + id bits). */
-int nmpm_migrate_pack(nmpm_handle h, void **send_left, size_t *n_left, void **send_right, size_t *n_right);
-int nmpm_migrate_unpack(nmpm_handle h, const void *recv_device, size_t n_recv);
-size_t nmpm_migrate_record_bytes(nmpm_handle h);
+int nmpm_slab_p2g(nmpm_handle h);
+/* send_left/send_right: device buffers of cap_records records each; d_counts: device int[4] =
+ * {n_left, n_right, n_kept, overflow} written by the kernel (n_left/n_right may exceed cap_records only
+ * together with overflow != 0, which is an error the caller must treat as fatal). */
+int nmpm_slab_grid_g2p(nmpm_handle h, void *send_left, void *send_right, size_t cap_records, int *d_counts);
+/* n_sent = records this slab packed in the last nmpm_slab_grid_g2p (n_left + n_right) */
+int nmpm_slab_unpack(nmpm_handle h, const void *recv_left, size_t n_from_left, const void *recv_right,
+                     size_t n_from_right, size_t n_sent);
+/* move the slab's ownership range (re-balancing); particles now outside migrate at the next step */
+int nmpm_slab_set_range(nmpm_handle h, int slab_x0, int slab_x1);
+/* d_hist: device int[res+1], incremented by the number of live particles per base.x */
+int nmpm_slab_histogram(nmpm_handle h, int *d_hist);
+/* global ids for the slab's particles (host array of n, creation order); particles() of the global
+ * simulation is assembled from nmpm_download_particles_slots by scattering on ids */
+int nmpm_set_ids(nmpm_handle h, const uint32_t *ids);
+/* slot order; arrays sized for nmpm_num_slots(h) entries; slots whose particle has just migrated away
+ * report id 0xFFFFFFFF (they are compacted away by the next nmpm_slab_p2g) */
+int nmpm_download_particles_slots(nmpm_handle h, float *x, float *v, float *F, float *C, float *Jp, uint32_t *ids);
+size_t nmpm_num_slots(nmpm_handle h);
 
 const char *nmpm_last_error(nmpm_handle h); /* h may be NULL: last creation error */
 const char *nmpm_build_info(void);          /* arch, compiler, date */

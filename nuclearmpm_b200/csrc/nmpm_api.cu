@@ -35,7 +35,13 @@ __global__ void __launch_bounds__(256) k_add_planes(float4* __restrict__ dst, co
 
 struct nmpm_sim {
     int dim = 0, model = 0, res = 0;
-    size_t n = 0, cells = 0;
+    size_t n = 0, cells = 0;  // n = live particles (slots [0,n) of store[cur] after a G2P)
+    size_t cap = 0;           // allocated particle slots
+    size_t n_store = 0;       // slab mode: entries in store[cur] incl. migrated-away ("gone") and just-received ones
+    size_t n_gone = 0;        // slab mode: entries of store[cur] whose key is kKeyGone
+    bool slab = false;
+    int gx0 = 0, gx1 = 0;     // slab mode: node planes [gx0, gx1+2) are cleared / updated (ownership range, or its union
+                              // with the previous one for the step right after nmpm_slab_set_range)
     MaterialParams P{};
     nmpm_options opt{};
     float E = 0, nu = 0, gravity = 0;
@@ -149,7 +155,7 @@ static int ensure_staging(nmpm_sim* h, size_t bytes) {
 }
 
 static int alloc_store(nmpm_sim* h, ParticleStore& S) {
-    const size_t n = h->n ? h->n : 1;
+    const size_t n = h->cap ? h->cap : 1;
     const int nq = (h->dim == 3) ? 6 : 3;
     for (int k = 0; k < nq; ++k) CUDA_TRY(h, cudaMalloc(&S.q[k], n * sizeof(float4)));
     CUDA_TRY(h, cudaMalloc(&S.s, n * sizeof(float)));
@@ -206,10 +212,23 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
         return NMPM_ERR_INVALID;
     }
     h->dim = dim, h->model = model, h->res = res, h->n = n;
+    h->n_store = n;
+    h->slab = h->opt.slab_x1 > 0;
+    h->cap = n;
+    if (h->slab) {
+        if (h->opt.slab_x0 < 0 || h->opt.slab_x1 <= h->opt.slab_x0 || h->opt.capacity < 0) {
+            g_create_error = "invalid slab range / capacity";
+            delete h;
+            return NMPM_ERR_INVALID;
+        }
+        if ((size_t) h->opt.capacity > n) h->cap = (size_t) h->opt.capacity;
+        h->gx0 = h->opt.slab_x0, h->gx1 = h->opt.slab_x1;
+        h->opt.use_graph = 0;   // particle counts change every step
+        h->opt.sort_every = 1;  // migrants are compacted away by the per-step sort
+    }
     h->E = E, h->nu = nu, h->gravity = gravity;
     h->device = h->opt.device;
     fill_params(h, dt, E, nu, gravity);
-    if (h->opt.slab_x1 <= 0) h->opt.slab_x1 = res + 1;
     const size_t n1 = (size_t) res + 1;
     h->cells = (dim == 3) ? n1 * n1 * n1 : n1 * n1;
     if (h->cells >= 0xFFFFFFFFull) {
@@ -242,7 +261,7 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
     CUDA_TRY(h, cudaMallocHost(&h->h_error, sizeof(int)));
     *h->h_error = 0;
     // sort workspace
-    const size_t nn = n ? n : 1;
+    const size_t nn = h->cap ? h->cap : 1;
     h->sort.ntiles = (uint32_t) ((nn + kSortTile - 1) / kSortTile);
     CUDA_TRY(h, cudaMalloc(&h->sort.keys_a, nn * sizeof(uint32_t)));
     CUDA_TRY(h, cudaMalloc(&h->sort.keys_b, nn * sizeof(uint32_t)));
@@ -267,7 +286,8 @@ void nmpm_default_options(nmpm_options* opt) {
     opt->p2g_variant = 0;
     opt->use_graph = 1;
     opt->slab_x0 = 0;
-    opt->slab_x1 = 0;  // 0 = res+1
+    opt->slab_x1 = 0;  // 0 = not a slab
+    opt->capacity = 0;
 }
 
 const char* nmpm_build_info(void) {
@@ -403,8 +423,9 @@ int nmpm_create_aos(int dim, int model, int res, float dt, float E, float nu, fl
     return NMPM_OK;
 }
 
-size_t nmpm_num_particles(nmpm_handle h) { return h ? h->n : 0; }
+size_t nmpm_num_particles(nmpm_handle h) { return h ? h->n_store - h->n_gone : 0; }
 size_t nmpm_grid_cells(nmpm_handle h) { return h ? h->cells : 0; }
+size_t nmpm_num_slots(nmpm_handle h) { return h ? h->n_store : 0; }
 int nmpm_key_tile_bits(nmpm_handle) { return kTileBits; }
 long long nmpm_launch_count(nmpm_handle h) { return h ? h->launches : 0; }
 
@@ -435,8 +456,8 @@ void* nmpm_get_stream(nmpm_handle h) { return h ? (void*) h->stream : nullptr; }
 // readers: P2G and G2P index the store through h->perm, and G2P writes the other store in sorted order.
 static int do_sort(nmpm_sim* h) {
     h->perm = nullptr;
-    if (h->n == 0) return NMPM_OK;
-    const uint32_t n = (uint32_t) h->n;
+    if (h->n_store == 0) return NMPM_OK;
+    const uint32_t n = (uint32_t) h->n_store;
     ParticleStore& S = h->store[h->cur];
     if (!h->keys_valid) {
         NMPM_DISPATCH_DIM(h, (k_cell_keys<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(
@@ -447,11 +468,30 @@ static int do_sort(nmpm_sim* h) {
     h->launches += radix_sort_pairs(h->sort, n, h->key_bits, h->stream, &ks, &perm);
     h->keys_valid = false;
     h->perm = perm;
+    // slab mode: particles that migrated away carry kKeyGone and sort last; they drop out here
+    h->n = h->n_store - h->n_gone;
+    h->n_gone = 0;
     return NMPM_OK;
 }
 
+// node range this sim clears and updates: the whole grid, or planes [x0, min(x1+2, n1)) of its slab
+static void grid_range(const nmpm_sim* h, size_t* first, size_t* count) {
+    const size_t plane = h->cells / (size_t) (h->res + 1);
+    if (!h->slab) {
+        *first = 0, *count = h->cells;
+        return;
+    }
+    const int n1 = h->res + 1;
+    const int p0 = h->gx0 < n1 ? h->gx0 : n1;
+    const int p1 = h->gx1 + 2 < n1 ? h->gx1 + 2 : n1;
+    *first = (size_t) p0 * plane;
+    *count = (size_t) (p1 > p0 ? p1 - p0 : 0) * plane;
+}
+
 static int do_p2g(nmpm_sim* h) {
-    CUDA_TRY(h, cudaMemsetAsync(h->grid, 0, h->cells * sizeof(float4), h->stream));
+    size_t g_first = 0, g_count = 0;
+    grid_range(h, &g_first, &g_count);
+    if (g_count) CUDA_TRY(h, cudaMemsetAsync(h->grid + g_first, 0, g_count * sizeof(float4), h->stream));
     h->grid_valid = true;
     if (h->n == 0) return NMPM_OK;
     const uint32_t n = (uint32_t) h->n;
@@ -469,13 +509,19 @@ static int do_p2g(nmpm_sim* h) {
 }
 
 static int do_grid_op(nmpm_sim* h) {
-    NMPM_DISPATCH_DIM(h, (k_grid_op<D><<<blocks_for(h->cells, 256), 256, 0, h->stream>>>(h->grid, h->cells, h->P)));
+    size_t g_first = 0, g_count = 0;
+    grid_range(h, &g_first, &g_count);
+    if (g_count == 0) return NMPM_OK;
+    NMPM_DISPATCH_DIM(h, (k_grid_op<D><<<blocks_for(g_count, 256), 256, 0, h->stream>>>(h->grid, g_first, g_count, h->P)));
     h->launches++;
     return NMPM_OK;
 }
 
-static int do_g2p(nmpm_sim* h) {
-    if (h->n == 0) return NMPM_OK;
+static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullptr, nullptr, 0, nullptr}) {
+    if (h->n == 0) {
+        h->n_store = 0;
+        return NMPM_OK;
+    }
     const uint32_t n = (uint32_t) h->n;
     ParticleStore& S = h->store[h->cur];
     ParticleStore& T = h->perm ? h->store[h->cur ^ 1] : S;
@@ -483,11 +529,12 @@ static int do_g2p(nmpm_sim* h) {
     const bool next_sorts = h->opt.sort_every > 0 && ((h->steps_done + 1) % h->opt.sort_every) == 0;
     uint32_t* keys_out = next_sorts ? h->sort.keys_a : nullptr;
     NMPM_DISPATCH(h, (k_g2p_gather<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(
-                         S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error)));
+                         S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error, mig)));
     h->launches++;
     if (h->perm) h->cur ^= 1;
     h->perm = nullptr;
     h->keys_valid = next_sorts;
+    h->n_store = h->n;  // the sorted write compacted the store
     return NMPM_OK;
 }
 
@@ -606,8 +653,17 @@ static int step_once(nmpm_sim* h) {
     return NMPM_OK;
 }
 
+static int not_for_slabs(nmpm_sim* h, const char* what) {
+    if (h->slab) {
+        h->last_error = std::string(what) + ": not available on a slab sim (use the nmpm_slab_* calls)";
+        return NMPM_ERR_INVALID;
+    }
+    return NMPM_OK;
+}
+
 int nmpm_advance(nmpm_handle h, int nsteps) {
     if (!h || nsteps < 0) return NMPM_ERR_INVALID;
+    if (int rc = not_for_slabs(h, "nmpm_advance")) return rc;
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (int rc = poll_error(h)) return rc;
     for (int s = 0; s < nsteps; ++s)
@@ -618,6 +674,7 @@ int nmpm_advance(nmpm_handle h, int nsteps) {
 
 int nmpm_phase(nmpm_handle h, int phase) {
     if (!h || phase < 0 || phase > 2) return NMPM_ERR_INVALID;
+    if (int rc = not_for_slabs(h, "nmpm_phase")) return rc;
     if (phase != h->phase_next) {
         h->last_error = "nmpm_phase: phases must be called in order p2g, grid_op, g2p";
         return NMPM_ERR_INVALID;
@@ -636,6 +693,7 @@ int nmpm_synchronize(nmpm_handle h) {
 
 int nmpm_download_particles(nmpm_handle h, float* x, float* v, float* F, float* C, float* Jp) {
     if (!h) return NMPM_ERR_INVALID;
+    if (int rc = not_for_slabs(h, "nmpm_download_particles")) return rc;
     CUDA_TRY(h, cudaSetDevice(h->device));
     const size_t n = h->n, D = (size_t) h->dim;
     if (n) {
@@ -652,7 +710,7 @@ int nmpm_download_particles(nmpm_handle h, float* x, float* v, float* F, float* 
         p += C ? n * D * D : 0;
         float* dJ = Jp ? p : nullptr;
         NMPM_DISPATCH_DIM(h, (k_export_soa<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(h->store[h->cur], (uint32_t) n,
-                                                                                         dx, dv, dF, dC, dJ)));
+                                                                                         dx, dv, dF, dC, dJ, nullptr, nullptr)));
         h->launches++;
         if (x) CUDA_TRY(h, cudaMemcpyAsync(x, dx, n * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         if (v) CUDA_TRY(h, cudaMemcpyAsync(v, dv, n * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -669,6 +727,7 @@ int nmpm_download_particles_aos(nmpm_handle h, void* particles_aos, size_t strid
     if (!h || !particles_aos) return NMPM_ERR_INVALID;
     const size_t rec = (h->dim == 3) ? 112 : 64;
     if (stride < rec || stride % 4) return NMPM_ERR_INVALID;
+    if (int rc = not_for_slabs(h, "nmpm_download_particles_aos")) return rc;
     CUDA_TRY(h, cudaSetDevice(h->device));
     const size_t n = h->n;
     if (n) {
@@ -728,6 +787,7 @@ int nmpm_download_grid_aos(nmpm_handle h, void* cells_aos, size_t stride, size_t
 int nmpm_upload_particles(nmpm_handle h, const float* x, const float* v, const float* F, const float* C,
                           const float* Jp) {
     if (!h || (h->n && !x)) return NMPM_ERR_INVALID;
+    if (int rc = not_for_slabs(h, "nmpm_upload_particles")) return rc;
     CUDA_TRY(h, cudaSetDevice(h->device));
     const size_t n = h->n, D = (size_t) h->dim;
     if (n == 0) return NMPM_OK;
@@ -903,18 +963,164 @@ int nmpm_grid_add_planes(nmpm_handle h, int x_plane, int planes, const void* dev
     CUDA_TRY(h, cudaGetLastError());
     return NMPM_OK;
 }
-size_t nmpm_migrate_record_bytes(nmpm_handle h) { return h ? 28 * sizeof(float) : 0; }
-int nmpm_migrate_pack(nmpm_handle h, void** send_left, size_t* n_left, void** send_right, size_t* n_right) {
-    if (!h) return NMPM_ERR_INVALID;
-    (void) send_left, (void) n_left, (void) send_right, (void) n_right;
-    h->last_error = "nmpm_migrate_pack: particle migration is not implemented yet (single-slab sims only)";
-    return NMPM_ERR_INVALID;
+size_t nmpm_migrate_record_bytes(nmpm_handle h) {
+    if (!h) return 0;
+    return (size_t) (2 * h->dim + 2 * h->dim * h->dim + 4) * sizeof(float);
 }
-int nmpm_migrate_unpack(nmpm_handle h, const void* recv_device, size_t n_recv) {
+
+static int slab_check(nmpm_sim* h, const char* what) {
     if (!h) return NMPM_ERR_INVALID;
-    (void) recv_device, (void) n_recv;
-    h->last_error = "nmpm_migrate_unpack: particle migration is not implemented yet (single-slab sims only)";
-    return NMPM_ERR_INVALID;
+    if (!h->slab) {
+        h->last_error = std::string(what) + ": the sim was not created as a slab (nmpm_options.slab_x1 == 0)";
+        return NMPM_ERR_INVALID;
+    }
+    return NMPM_OK;
+}
+
+int nmpm_slab_p2g(nmpm_handle h) {
+    if (int rc = slab_check(h, "nmpm_slab_p2g")) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (int rc = poll_error(h)) return rc;
+    if (h->phase_next != 0) {
+        h->last_error = "nmpm_slab_p2g: called in the middle of a step";
+        return NMPM_ERR_INVALID;
+    }
+    if (int rc = do_sort(h)) return rc;
+    if (int rc = do_p2g(h)) return rc;
+    h->phase_next = 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return NMPM_OK;
+}
+
+int nmpm_slab_grid_g2p(nmpm_handle h, void* send_left, void* send_right, size_t cap_records, int* d_counts) {
+    if (int rc = slab_check(h, "nmpm_slab_grid_g2p")) return rc;
+    if (!send_left || !send_right || !d_counts || cap_records > 0xFFFFFFF0ull) return NMPM_ERR_INVALID;
+    if (h->phase_next != 1) {
+        h->last_error = "nmpm_slab_grid_g2p: nmpm_slab_p2g must come first";
+        return NMPM_ERR_INVALID;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemsetAsync(d_counts, 0, 4 * sizeof(int), h->stream));
+    if (int rc = do_grid_op(h)) return rc;
+    MigrateArgs mig{h->opt.slab_x0, h->opt.slab_x1, (float*) send_left, (float*) send_right, (uint32_t) cap_records,
+                    d_counts};
+    if (int rc = do_g2p(h, mig)) return rc;
+    h->steps_done++;
+    h->phase_next = 0;
+    h->gx0 = h->opt.slab_x0, h->gx1 = h->opt.slab_x1;  // every particle now obeys the current ownership range
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_error, h->d_error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    return NMPM_OK;
+}
+
+int nmpm_slab_unpack(nmpm_handle h, const void* recv_left, size_t n_from_left, const void* recv_right,
+                     size_t n_from_right, size_t n_sent) {
+    if (int rc = slab_check(h, "nmpm_slab_unpack")) return rc;
+    if ((n_from_left && !recv_left) || (n_from_right && !recv_right) || n_sent > h->n_store) return NMPM_ERR_INVALID;
+    if (h->phase_next != 0 || h->n_gone != 0) {
+        h->last_error = "nmpm_slab_unpack: must follow nmpm_slab_grid_g2p";
+        return NMPM_ERR_INVALID;
+    }
+    if (h->n_store + n_from_left + n_from_right > h->cap) {
+        h->last_error = "nmpm_slab_unpack: particle capacity exceeded (raise nmpm_options.capacity)";
+        return NMPM_ERR_INVALID;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    ParticleStore& T = h->store[h->cur];
+    const void* src[2] = {recv_left, recv_right};
+    const size_t cnt[2] = {n_from_left, n_from_right};
+    for (int s = 0; s < 2; ++s) {
+        if (!cnt[s]) continue;
+        NMPM_DISPATCH_DIM(h, (k_unpack_records<D><<<blocks_for(cnt[s], 256), 256, 0, h->stream>>>(
+                                 (const float*) src[s], (uint32_t) cnt[s], (uint32_t) h->n_store, T, h->P,
+                                 h->tiles_per_axis, h->sort.keys_a)));
+        h->launches++;
+        h->n_store += cnt[s];
+    }
+    h->n_gone = n_sent;
+    CUDA_TRY(h, cudaGetLastError());
+    return NMPM_OK;
+}
+
+int nmpm_slab_set_range(nmpm_handle h, int slab_x0, int slab_x1) {
+    if (int rc = slab_check(h, "nmpm_slab_set_range")) return rc;
+    if (slab_x0 < 0 || slab_x1 <= slab_x0 || h->phase_next != 0) return NMPM_ERR_INVALID;
+    // particles keep their current owner until the next G2P hands them over: until then the grid
+    // range is the union of the old and the new ownership range
+    h->gx0 = slab_x0 < h->gx0 ? slab_x0 : h->gx0;
+    h->gx1 = slab_x1 > h->gx1 ? slab_x1 : h->gx1;
+    h->opt.slab_x0 = slab_x0;
+    h->opt.slab_x1 = slab_x1;
+    return NMPM_OK;
+}
+
+int nmpm_slab_histogram(nmpm_handle h, int* d_hist) {
+    if (!h || !d_hist) return NMPM_ERR_INVALID;
+    if (h->n_gone != 0 || h->phase_next != 0) {
+        h->last_error = "nmpm_slab_histogram: call between steps, before nmpm_slab_unpack";
+        return NMPM_ERR_INVALID;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->n_store == 0) return NMPM_OK;
+    NMPM_DISPATCH_DIM(h, (k_histogram_x<D><<<blocks_for(h->n_store, 256), 256, 0, h->stream>>>(
+                             h->store[h->cur], (uint32_t) h->n_store, h->P, d_hist)));
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return NMPM_OK;
+}
+
+int nmpm_set_ids(nmpm_handle h, const uint32_t* ids) {
+    if (!h || (h->n && !ids)) return NMPM_ERR_INVALID;
+    if (h->steps_done != 0 || h->n_gone != 0 || h->n_store != h->n) {
+        h->last_error = "nmpm_set_ids: only right after creation";
+        return NMPM_ERR_INVALID;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->n == 0) return NMPM_OK;
+    if (int rc = ensure_staging(h, h->n * sizeof(uint32_t))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->staging, ids, h->n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    NMPM_DISPATCH_DIM(h, (k_set_ids<D><<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->store[h->cur], (uint32_t) h->n,
+                                                                                     (const uint32_t*) h->staging)));
+    h->launches++;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NMPM_OK;
+}
+
+int nmpm_download_particles_slots(nmpm_handle h, float* x, float* v, float* F, float* C, float* Jp, uint32_t* ids) {
+    if (!h || !ids) return NMPM_ERR_INVALID;
+    if (h->phase_next != 0) {
+        h->last_error = "nmpm_download_particles_slots: not in the middle of a step";
+        return NMPM_ERR_INVALID;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = h->n_store, D = (size_t) h->dim;
+    if (n) {
+        const size_t words = n * (2 * D + 2 * D * D + 2);
+        if (int rc = ensure_staging(h, words * sizeof(float))) return rc;
+        float* p = h->staging;
+        float* dx = p;
+        p += n * D;
+        float* dv = p;
+        p += n * D;
+        float* dF = p;
+        p += n * D * D;
+        float* dC = p;
+        p += n * D * D;
+        float* dJ = p;
+        p += n;
+        uint32_t* did = (uint32_t*) p;
+        NMPM_DISPATCH_DIM(h, (k_export_soa<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(h->store[h->cur], (uint32_t) n,
+                                                                                         dx, dv, dF, dC, dJ, did,
+                                                                                         h->n_gone ? h->sort.keys_a : nullptr)));
+        h->launches++;
+        if (x) CUDA_TRY(h, cudaMemcpyAsync(x, dx, n * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        if (v) CUDA_TRY(h, cudaMemcpyAsync(v, dv, n * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        if (F) CUDA_TRY(h, cudaMemcpyAsync(F, dF, n * D * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        if (C) CUDA_TRY(h, cudaMemcpyAsync(C, dC, n * D * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        if (Jp) CUDA_TRY(h, cudaMemcpyAsync(Jp, dJ, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(ids, did, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    return sync_and_check(h);
 }
 
 }  // extern "C"

@@ -23,6 +23,43 @@ __device__ __forceinline__ void red_add_f32x4(float4* addr, float4 v) {
                  : "memory");
 }
 
+// Keys above every valid cell key.  A particle whose stencil left the grid (the step is flagged, Q5)
+// sorts after all valid particles; a particle that migrated to a neighbouring slab sorts last of all,
+// so that the first n_live entries of the sorted order are exactly the particles that are still here.
+constexpr uint32_t kKeyOutOfGrid = 0xFFFFFFFEu;
+constexpr uint32_t kKeyGone = 0xFFFFFFFFu;
+
+// Slab migration (multi-GPU, include/nmpm.h): G2P hands particles whose next base.x is outside
+// [x0, x1) to the left / right send buffer as Particle<dim> AoS records.  left == nullptr: disabled.
+struct MigrateArgs {
+    int x0, x1;
+    float* left;
+    float* right;
+    uint32_t cap;
+    int* counts;  // {n_left, n_right, n_kept, overflow}
+};
+
+template <int D>
+struct RecordTraits {
+    static constexpr int WORDS = 2 * D + 2 * D * D + 4;  // 16 (2D) / 28 (3D): sizeof(Particle<dim>) / 4
+};
+
+template <int D>
+__device__ __forceinline__ void write_record(float* __restrict__ r, const PState<D>& p, float2 mv, uint32_t id) {
+    float w[RecordTraits<D>::WORDS];
+#pragma unroll
+    for (int d = 0; d < D; ++d) w[d] = p.x[d], w[D + d] = p.v[d];
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) w[2 * D + k] = p.F.m[k], w[2 * D + D * D + k] = p.C.m[k];
+    w[2 * D + 2 * D * D] = p.Jp;
+    w[2 * D + 2 * D * D + 1] = mv.x;
+    w[2 * D + 2 * D * D + 2] = mv.y;
+    w[2 * D + 2 * D * D + 3] = __uint_as_float(id);
+    float4* r4 = reinterpret_cast<float4*>(r);
+#pragma unroll
+    for (int k = 0; k < RecordTraits<D>::WORDS / 4; ++k) r4[k] = make_float4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+}
+
 // ---- K0a: cell keys from current positions -------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(256) k_cell_keys(ParticleStore S, uint32_t n, MaterialParams P, int tiles_per_axis,
@@ -43,7 +80,7 @@ __global__ void __launch_bounds__(256) k_cell_keys(ParticleStore S, uint32_t n, 
     }
     if (bad) {
         atomicOr(error_flag, 1);
-        keys[i] = 0xFFFFFFFFu;
+        keys[i] = kKeyOutOfGrid;
     } else {
         keys[i] = cell_key<D>(b, tiles_per_axis);
     }
@@ -131,9 +168,11 @@ __global__ void __launch_bounds__(128) k_p2g_scatter(ParticleStore S, const uint
 // One thread per node, float4 in / float4 out.  Normalise by mass, gravity on y (Q7), clamp to
 // ±0.9 dx/dt, then the sticky 3-node walls which zero the WHOLE node incl. its mass (Q6).
 template <int D>
-__global__ void __launch_bounds__(256) k_grid_op(float4* __restrict__ grid, size_t cells, MaterialParams P) {
-    const size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= cells) return;
+__global__ void __launch_bounds__(256) k_grid_op(float4* __restrict__ grid, size_t first, size_t cells,
+                                                 MaterialParams P) {
+    // nodes [first, first + cells): the whole grid, or the node planes of one x-slab
+    const size_t idx = first + (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= first + cells) return;
     float4 g = grid[idx];
     // untouched node (all zero): normalisation is skipped (mass == 0) and the sticky walls only act on
     // non-zero velocities, so the node stays as it is — leave before any index arithmetic
@@ -225,7 +264,7 @@ template <int D, int MODEL>
 __global__ void __launch_bounds__(128) k_g2p_gather(ParticleStore S, ParticleStore T, const uint32_t* __restrict__ perm,
                                                     uint32_t n, MaterialParams P, const float4* __restrict__ grid,
                                                     uint32_t* __restrict__ keys_out, int tiles_per_axis,
-                                                    int* __restrict__ error_flag) {
+                                                    int* __restrict__ error_flag, MigrateArgs mig) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t src = perm ? __ldg(perm + i) : i;
@@ -300,9 +339,15 @@ __global__ void __launch_bounds__(128) k_g2p_gather(ParticleStore S, ParticleSto
     }
     g2p_update<D, MODEL>(p, Cn, vn, P);
     store_state<D>(T, i, p);
+    float2 mv = make_float2(0.0f, 0.0f);
+    uint32_t pid = 0;
+    if (perm || mig.left) {
+        mv = __ldg(S.mv + src);
+        pid = __ldg(S.id + src);
+    }
     if (perm) {
-        T.mv[i] = __ldg(S.mv + src);
-        T.id[i] = __ldg(S.id + src);
+        T.mv[i] = mv;
+        T.id[i] = pid;
     }
     if (keys_out) {
         int b[D];
@@ -314,8 +359,65 @@ __global__ void __launch_bounds__(128) k_g2p_gather(ParticleStore S, ParticleSto
             bad = bad || !s.ok;
         }
         // an out-of-grid position is flagged by the next step's P2G/G2P (that is when the reference throws)
-        keys_out[i] = bad ? 0xFFFFFFFFu : cell_key<D>(b, tiles_per_axis);
+        uint32_t key = bad ? kKeyOutOfGrid : cell_key<D>(b, tiles_per_axis);
+        if (mig.left && !bad && (b[0] < mig.x0 || b[0] >= mig.x1)) {
+            const int side = (b[0] < mig.x0) ? 0 : 1;
+            const uint32_t slot = (uint32_t) atomicAdd(mig.counts + side, 1);
+            if (slot < mig.cap) {
+                write_record<D>((side ? mig.right : mig.left) + (size_t) slot * RecordTraits<D>::WORDS, p, mv, pid);
+                key = kKeyGone;
+            } else {
+                atomicExch(mig.counts + 3, 1);  // send buffer overflow: fatal for the caller
+            }
+        }
+        keys_out[i] = key;
     }
+}
+
+// slab migration, receiving side: append records to slots [first, first + count) and bin them
+template <int D>
+__global__ void __launch_bounds__(256) k_unpack_records(const float* __restrict__ rec, uint32_t count, uint32_t first,
+                                                        ParticleStore T, MaterialParams P, int tiles_per_axis,
+                                                        uint32_t* __restrict__ keys) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const float* r = rec + (size_t) j * RecordTraits<D>::WORDS;
+    PState<D> p;
+#pragma unroll
+    for (int d = 0; d < D; ++d) p.x[d] = r[d], p.v[d] = r[D + d];
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) p.F.m[k] = r[2 * D + k], p.C.m[k] = r[2 * D + D * D + k];
+    p.Jp = r[2 * D + 2 * D * D];
+    const uint32_t i = first + j;
+    store_state<D>(T, i, p);
+    T.mv[i] = make_float2(r[2 * D + 2 * D * D + 1], r[2 * D + 2 * D * D + 2]);
+    T.id[i] = __float_as_uint(r[2 * D + 2 * D * D + 3]);
+    int b[D];
+    bool bad = false;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const Stencil1 s = stencil_axis(p.x[d], P.inv_dx, P.res);
+        b[d] = s.base;
+        bad = bad || !s.ok;
+    }
+    keys[i] = bad ? kKeyOutOfGrid : cell_key<D>(b, tiles_per_axis);
+}
+
+// live particles per base.x (re-balancing of the slab boundaries)
+template <int D>
+__global__ void __launch_bounds__(256) k_histogram_x(ParticleStore S, uint32_t n, MaterialParams P, int* __restrict__ hist) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x[D];
+    load_position<D>(S, i, x);
+    const Stencil1 s = stencil_axis(x[0], P.inv_dx, P.res);
+    atomicAdd(hist + min(max(s.base, 0), P.res), 1);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_set_ids(ParticleStore S, uint32_t n, const uint32_t* __restrict__ ids) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) S.id[i] = ids[S.id[i]];
 }
 
 // ---- K5: import / export between the interchange layouts and the device store ---------------
@@ -381,12 +483,16 @@ __global__ void __launch_bounds__(256) k_import_soa(const float* __restrict__ x,
 template <int D>
 __global__ void __launch_bounds__(256) k_export_soa(ParticleStore S, uint32_t n, float* __restrict__ x,
                                                     float* __restrict__ v, float* __restrict__ F, float* __restrict__ C,
-                                                    float* __restrict__ Jp) {
+                                                    float* __restrict__ Jp, uint32_t* __restrict__ ids_out,
+                                                    const uint32_t* __restrict__ keys) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     PState<D> p;
     load_for_p2g<D>(S, i, p);
-    const size_t o = S.id[i];
+    // ids_out != nullptr: slot order + the id of each slot (slab download); else input order.
+    // keys != nullptr: slots whose particle migrated away (kKeyGone) report id 0xFFFFFFFF.
+    const size_t o = ids_out ? (size_t) i : (size_t) S.id[i];
+    if (ids_out) ids_out[i] = (keys && keys[i] == kKeyGone) ? 0xFFFFFFFFu : S.id[i];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         if (x) x[o * D + d] = p.x[d];

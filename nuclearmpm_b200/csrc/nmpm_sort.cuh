@@ -164,7 +164,8 @@ struct SortWorkspace {
 // (they alias ws buffers).  `key_bits` = number of significant key bits.  Returns launches issued.
 inline int radix_sort_pairs(SortWorkspace& ws, uint32_t n, int key_bits, cudaStream_t st, uint32_t** keys_sorted,
                             uint32_t** perm) {
-    const int passes = (key_bits + 7) / 8;
+    // one spare bit above the cell keys so that the special keys (out of grid, migrated away) stay on top
+    const int passes = (key_bits + 8) / 8;
     uint32_t *kin = ws.keys_a, *kout = ws.keys_b, *vin = nullptr, *vout = ws.vals_a;
     uint32_t* vother = ws.vals_b;
     int launches = 0;

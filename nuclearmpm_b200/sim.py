@@ -45,7 +45,7 @@ class MaterialModel(enum.IntEnum):
 
 class Options(ct.Structure):
     _fields_ = [("device", ct.c_int), ("sort_every", ct.c_int), ("p2g_variant", ct.c_int), ("use_graph", ct.c_int),
-                ("slab_x0", ct.c_int), ("slab_x1", ct.c_int), ("reserved", ct.c_int * 10)]
+                ("slab_x0", ct.c_int), ("slab_x1", ct.c_int), ("capacity", ct.c_int), ("reserved", ct.c_int * 9)]
 
 
 def lib_path() -> Path:
@@ -103,8 +103,14 @@ def load_library():
     sig("nmpm_grid_plane_ptr", vp, [vp, ci])
     sig("nmpm_grid_plane_bytes", sz, [vp])
     sig("nmpm_grid_add_planes", ci, [vp, ci, ci, vp])
-    sig("nmpm_migrate_pack", ci, [vp, ct.POINTER(vp), ct.POINTER(sz), ct.POINTER(vp), ct.POINTER(sz)])
-    sig("nmpm_migrate_unpack", ci, [vp, vp, sz])
+    sig("nmpm_slab_p2g", ci, [vp])
+    sig("nmpm_slab_grid_g2p", ci, [vp, vp, vp, sz, vp])
+    sig("nmpm_slab_unpack", ci, [vp, vp, sz, vp, sz, sz])
+    sig("nmpm_slab_set_range", ci, [vp, ci, ci])
+    sig("nmpm_slab_histogram", ci, [vp, vp])
+    sig("nmpm_set_ids", ci, [vp, _u32p])
+    sig("nmpm_download_particles_slots", ci, [vp] + [_fp] * 5 + [_u32p])
+    sig("nmpm_num_slots", sz, [vp])
     sig("nmpm_migrate_record_bytes", sz, [vp])
     sig("nmpm_last_error", ct.c_char_p, [vp])
     sig("nmpm_build_info", ct.c_char_p, [])
@@ -153,7 +159,8 @@ class MPMSimulation:
 
     def __init__(self, particles, model, res: int = 64, dt: float = 1e-4, E: float = 1e4, nu: float = 0.2,
                  gravity: float = -100.0, *, v=None, F=None, C=None, Jp=None, mass=None, volume=None,
-                 device: int = 0, sort_every: int = 1, p2g_variant: int = 0, slab=None):
+                 device: int = 0, sort_every: int = 1, p2g_variant: int = 0, slab=None, capacity: int = 0,
+                 ids=None):
         self._L = load_library()
         x = _f32(particles)
         if x.ndim != 2 or x.shape[1] not in (2, 3):
@@ -166,6 +173,7 @@ class MPMSimulation:
         opt.device, opt.sort_every, opt.p2g_variant = device, sort_every, p2g_variant
         if slab is not None:
             opt.slab_x0, opt.slab_x1 = slab
+            opt.capacity = int(capacity)
         arrs = [x, _f32(v, (n, d)), _f32(F, (n, d, d)), _f32(C, (n, d, d)), _f32(Jp, (n,)), _f32(mass, (n,)),
                 _f32(volume, (n,))]
         h = C_void_p()
@@ -177,6 +185,10 @@ class MPMSimulation:
         mu, lam = ct.c_float(), ct.c_float()
         self._L.nmpm_lame(self._h, C_byref(mu), C_byref(lam))
         self.mu_0, self.lambda_0 = mu.value, lam.value
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.uint32)
+            assert ids.shape == (n,)
+            self._check(self._L.nmpm_set_ids(self._h, ids.ctypes.data_as(_u32p)), "nmpm_set_ids")
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -217,6 +229,21 @@ class MPMSimulation:
         self._check(self._L.nmpm_download_particles(self._h, *[_p(out[k]) for k in ("x", "v", "F", "C", "Jp")]),
                     "nmpm_download_particles")
         return out
+
+    def num_particles(self) -> int:
+        return int(self._L.nmpm_num_particles(self._h))
+
+    def particles_slots(self) -> dict:
+        """Slab sims: the live particles in device slot order plus their global ids."""
+        n, d = int(self._L.nmpm_num_slots(self._h)), self.dim
+        out = dict(x=np.empty((n, d), np.float32), v=np.empty((n, d), np.float32),
+                   F=np.empty((n, d, d), np.float32), C=np.empty((n, d, d), np.float32),
+                   Jp=np.empty((n,), np.float32), ids=np.empty((n,), np.uint32))
+        self._check(self._L.nmpm_download_particles_slots(self._h, *[_p(out[k]) for k in ("x", "v", "F", "C", "Jp")],
+                                                          out["ids"].ctypes.data_as(_u32p)),
+                    "nmpm_download_particles_slots")
+        live = out["ids"] != 0xFFFFFFFF  # slots of particles that have just migrated away
+        return out if live.all() else {k: a[live] for k, a in out.items()}
 
     def positions(self) -> np.ndarray:
         x = np.empty((self.n, self.dim), np.float32)

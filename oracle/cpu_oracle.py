@@ -83,6 +83,7 @@ class _Lib:
         self.oob_events = fn("oob_events", C.c_long, [])
         self.oob_reset = fn("oob_reset", None, [])
         if kind == "port":
+            self.set_grid = fn("set_grid", C.c_long, [C.c_void_p, _fp, _fp])
             self.cell_keys = fn("cell_keys", C.c_long,
                                 [C.c_int, C.c_int, C.c_long, _fp, C.c_int, C.c_int,
                                  C.POINTER(C.c_int32), C.POINTER(C.c_uint32)])
@@ -157,6 +158,11 @@ class CpuSim:
         if got == 0:
             return gv[:0], gm[:0]
         return gv, gm
+
+    def set_grid(self, gv, gm) -> None:
+        """port only: overwrite the grid between phases (slab protocol tests)."""
+        gv, gm = _f32(gv), _f32(gm)
+        assert self.L.set_grid(self.h, _p(gv), _p(gm)) == gm.size
 
     def lame(self):
         a, b = C.c_float(), C.c_float()

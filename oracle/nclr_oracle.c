@@ -553,6 +553,15 @@ long nclr_oracle_get_grid(void *sv, float *gv, float *gm) {
     return s->ncells;
 }
 
+/* test hook for the slab (multi-GPU) protocol tests: overwrite the grid between phases */
+long nclr_oracle_set_grid(void *sv, const float *gv, const float *gm) {
+    struct nclr_oracle_sim *s = (struct nclr_oracle_sim *) sv;
+    if (!s->gv) return 0;
+    memcpy(s->gv, gv, sizeof(float) * (size_t) (s->ncells * s->dim));
+    memcpy(s->gm, gm, sizeof(float) * (size_t) s->ncells);
+    return s->ncells;
+}
+
 void nclr_oracle_lame(void *sv, float *mu0, float *lambda0) {
     const struct nclr_oracle_sim *s = (const struct nclr_oracle_sim *) sv;
     *mu0 = s->mu_0;
@@ -611,7 +620,7 @@ long nclr_oracle_cell_keys(int dim, int res, long n, const float *x, int mode, i
         if (!keys) continue;
         uint32_t key;
         if (out) {
-            key = 0xFFFFFFFFu; /* sorted last; the solver raises before using it */
+            key = 0xFFFFFFFEu; /* sorted after every valid key (0xFFFFFFFF = migrated away, slab mode); the solver raises before using it */
         } else if (mode == 0) {
             key = (dim == 3) ? (uint32_t) ((b[0] * n1 + b[1]) * n1 + b[2]) : (uint32_t) (b[0] * n1 + b[1]);
         } else {

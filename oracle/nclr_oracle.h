@@ -38,6 +38,7 @@ double nclr_oracle_time_advance(void *sim, int nsteps);
 long nclr_oracle_num_particles(void *sim);
 void nclr_oracle_get_particles(void *sim, float *x, float *v, float *F, float *C, float *Jp);
 long nclr_oracle_get_grid(void *sim, float *gv, float *gm);
+long nclr_oracle_set_grid(void *sim, const float *gv, const float *gm); /* port only: slab protocol tests */
 void nclr_oracle_lame(void *sim, float *mu0, float *lambda0);
 void nclr_oracle_svd(int dim, const float *a, float *U, float *sig, float *V);
 void nclr_oracle_polar(int dim, const float *m, float *R, float *S);

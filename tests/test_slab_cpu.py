@@ -1,0 +1,113 @@
+"""Multi-GPU slab path, host side, without GPUs: world_size-2/3 gloo runs of slab.SlabSimulation with the
+oracle-backed engine (tests/slab_oracle_engine.py) must reproduce the single-domain oracle."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+from nuclearmpm_b200 import slab  # noqa: E402
+from oracle import cpu_oracle as co  # noqa: E402
+
+
+def test_balanced_bounds_and_base_x():
+    hist = np.zeros(65, np.int64)
+    hist[20:40] = 100
+    b = slab.balanced_bounds(hist, 4)
+    assert b[0] == 0 and b[-1] == 65 and all(b[i + 1] - b[i] >= 4 for i in range(4))
+    per = [hist[b[i]:b[i + 1]].sum() for i in range(4)]
+    assert max(per) - min(per) <= 100
+    # degenerate: everything in one plane still yields legal slabs
+    hist2 = np.zeros(33, np.int64)
+    hist2[5] = 1000
+    b2 = slab.balanced_bounds(hist2, 8)
+    assert b2[0] == 0 and b2[-1] == 33 and all(b2[i + 1] - b2[i] >= 4 for i in range(8))
+    with pytest.raises(ValueError):
+        slab.balanced_bounds(np.zeros(9), 4)
+    # ownership uses the solver's own base computation (bit-exact vs the oracle's binning)
+    rng = np.random.default_rng(1)
+    x = rng.uniform(0.05, 0.95, size=(2000, 3)).astype(np.float32)
+    base, _, bad = co.cell_keys(x, 64, mode=0)
+    assert bad == 0 and (slab.base_x(x, 64) == base[:, 0]).all()
+    # limited_shift moves towards the target by at most max_shift and keeps widths
+    out = slab.limited_shift([0, 10, 20, 33], [0, 4, 30, 33], 2)
+    assert out == [0, 8, 22, 33]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, dim, model, res, steps, rebalance, q):
+    import torch.distributed as dist
+    from slab_oracle_engine import OracleSlabEngine
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x, v = scene(dim)
+        sim = slab.SlabSimulation(x, model, res, engine_factory=OracleSlabEngine, rebalance_every=rebalance, v=v)
+        counts = []
+        for _ in range(steps):
+            sim.step()
+            counts.append(sim.num_local())
+        out = sim.particles(dst=0)
+        info = dict(bounds=sim.bounds, migrated=sim.migrated, counts=counts)
+        allinfo = [None] * world if rank == 0 else None
+        dist.gather_object(info, allinfo, dst=0)
+        if rank == 0:
+            q.put((out, allinfo))
+    finally:
+        dist.destroy_process_group()
+
+
+def scene(dim):
+    # a block moving to +x so that particles cross slab boundaries within a few steps
+    x = co.cube(2, 24, 0.3, 0.6) if dim == 2 else co.cube(3, 10, 0.35, 0.6)
+    v = np.zeros_like(x)
+    v[:, 0] = 100.0 if dim == 2 else 60.0  # 0.64 / 0.19 cells per step, below the 0.9-cell grid clamp
+    return x, v
+
+
+@pytest.mark.parametrize("dim,model,world,rebalance", [(2, co.SNOW, 2, 0), (3, co.JELLY, 2, 0), (3, co.SNOW, 3, 2),
+                                                        (2, co.LIQUID, 3, 3)])
+def test_slab_protocol_matches_single_domain_oracle(dim, model, world, rebalance):
+    # free-running horizons: 3D snow decorrelates from step 4 (Q1 explosion)
+    res, steps = (64, 12) if dim == 2 else (32, 3 if model == co.SNOW else 6)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, dim, model, res, steps, rebalance, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, infos = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x, v = scene(dim)
+    ref = co.CpuSim(x, model, res, v=v)
+    ref.advance(steps)
+    r = ref.particles()
+    vmax = max(1.0, float(np.abs(r["v"]).max()))
+    cmax = max(1.0, float(np.abs(r["C"]).max()))
+    # same algorithm, different summation order on the shared planes only
+    k = steps
+    assert np.abs(got["x"] - r["x"]).max() <= 2.4e-7 * k
+    assert np.abs(got["v"] - r["v"]).max() <= 1e-5 * vmax * k
+    assert np.abs(got["F"] - r["F"]).max() <= 2e-5 * k
+    # C = 4 inv_dx sum w v dpos^T is a difference of O(4 res |v|) terms: a few ulp of those is the floor
+    assert np.abs(got["C"] - r["C"]).max() <= (5e-5 * cmax + 1e-6 * 4 * res * vmax) * k
+    assert np.abs(got["Jp"] - r["Jp"]).max() <= 1e-4 * k
+    assert sum(i["counts"][-1] for i in infos) == len(x)
+    print("slab bounds", [i["bounds"] for i in infos][0], "migrated", [i["migrated"] for i in infos],
+          "final counts", [i["counts"][-1] for i in infos])
+    if rebalance or dim == 2:
+        assert sum(i["migrated"] for i in infos) > 0  # the migration path was exercised

@@ -1,0 +1,145 @@
+"""Slab (multi-GPU) path on the device.
+
+* one GPU, two logical slabs in one process: the nmpm_slab_* C-ABI calls (ghost-plane reduction, migration
+  pack/unpack, sorted compaction) against the single-domain CUDA path and the oracle;
+* >= 2 GPUs (skipped otherwise): slab.SlabSimulation over NCCL, one process per GPU.
+"""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "tests"))
+
+import nuclearmpm_b200 as nm  # noqa: E402
+from nuclearmpm_b200 import slab  # noqa: E402
+from oracle import cpu_oracle as co  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def moving_block(dim, res):
+    x = co.cube(2, 40, 0.3, 0.6) if dim == 2 else co.cube(3, 24, 0.3, 0.6)
+    v = np.zeros_like(x)
+    v[:, 0] = 100.0 if dim == 2 else 60.0
+    return x, v
+
+
+def check(got, ref, k, res):
+    vmax = max(1.0, float(np.abs(ref["v"]).max()))
+    cmax = max(1.0, float(np.abs(ref["C"]).max()))
+    assert np.abs(got["x"] - ref["x"]).max() <= 2.4e-7 * k
+    assert np.abs(got["v"] - ref["v"]).max() <= 1e-5 * vmax * k
+    assert np.abs(got["F"] - ref["F"]).max() <= 2e-5 * k
+    assert np.abs(got["C"] - ref["C"]).max() <= (5e-5 * cmax + 1e-6 * 4 * res * vmax) * k
+    assert np.abs(got["Jp"] - ref["Jp"]).max() <= 1e-4 * k
+
+
+@pytest.mark.parametrize("dim,model", [(2, co.SNOW), (3, co.JELLY), (3, co.LIQUID), (3, co.SNOW)])
+def test_two_logical_slabs_on_one_gpu(dim, model):
+    import torch
+    res = 64 if dim == 2 else 32
+    steps = 10 if dim == 2 else (3 if model == co.SNOW else 6)
+    x, v = moving_block(dim, res)
+    bx = slab.base_x(x, res)
+    hist = np.bincount(bx, minlength=res + 1)
+    b = slab.balanced_bounds(hist, 2)
+    ranges = [(0, b[1]), (b[1], res + 1 + (1 << 20))]
+    eng = []
+    for (x0, x1) in ranges:
+        mine = np.nonzero((bx >= x0) & (bx < x1))[0]
+        eng.append(slab.GpuSlabEngine(x[mine], mine.astype(np.uint32), model, res, 1e-4, 1e4, 0.2, -100.0, (x0, x1),
+                                      len(x) + 1024, 0, v=v[mine]))
+    W, cap = eng[0].rec_words, len(x)
+    send = [[e.new_buffer(cap * W), e.new_buffer(cap * W)] for e in eng]
+    counts = [e.new_buffer(4, "int32") for e in eng]
+    migrated = 0
+    for _ in range(steps):
+        for e in eng:
+            e.p2g()
+        from_right = eng[1].plane_view(b[1], 2).clone()
+        from_left = eng[0].plane_view(b[1], 2).clone()
+        eng[0].add_planes(b[1], 2, from_right)
+        eng[1].add_planes(b[1], 2, from_left)
+        # the shared planes now hold identical sums on both sides
+        torch.cuda.synchronize()
+        assert torch.equal(eng[0].plane_view(b[1], 2), eng[1].plane_view(b[1], 2))
+        for i, e in enumerate(eng):
+            e.grid_g2p(send[i][0], send[i][1], cap, counts[i])
+        c = [t.cpu().numpy() for t in counts]
+        assert c[0][3] == 0 and c[1][3] == 0 and c[0][0] == 0 and c[1][1] == 0
+        eng[0].unpack(send[1][0], 0, send[1][0], int(c[1][0]), int(c[0][0] + c[0][1]))  # left slab receives from the right
+        eng[1].unpack(send[0][1], int(c[0][1]), send[0][1], 0, int(c[1][0] + c[1][1]))  # right slab receives from the left
+        migrated += int(c[0][1] + c[1][0])
+        assert eng[0].num_particles() + eng[1].num_particles() == len(x)
+    assert migrated > 0
+    got = {k: np.empty_like(a) for k, a in dict(x=x, v=v, F=np.empty((len(x), dim, dim), np.float32),
+                                                C=np.empty((len(x), dim, dim), np.float32),
+                                                Jp=np.empty(len(x), np.float32)).items()}
+    seen = np.zeros(len(x), int)
+    for e in eng:
+        part = e.download_slots()
+        ids = part["ids"].astype(np.int64)
+        seen[ids] += 1
+        for k in got:
+            got[k][ids] = part[k]
+    assert (seen == 1).all()
+    ref = co.CpuSim(x, model, res, v=v)
+    ref.advance(steps)
+    check(got, ref.particles(), steps, res)
+    # and the single-domain CUDA path agrees too
+    one = nm.MPMSimulation(x, model, res, v=v)
+    one.advance(steps)
+    check(got, one.particles(), steps, res)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _nccl_worker(rank, world, port, dim, model, res, steps, rebalance, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        x, v = moving_block(dim, res)
+        sim = slab.SlabSimulation(x, model, res, device=rank, rebalance_every=rebalance, v=v)
+        sim.advance(steps)
+        out = sim.particles(dst=0)
+        if rank == 0:
+            q.put((out, sim.migrated))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dim,model,rebalance", [(3, co.JELLY, 0), (3, co.SNOW, 2), (2, co.LIQUID, 3)])
+def test_slab_simulation_over_nccl(dim, model, rebalance):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    res = 64 if dim == 2 else 32
+    steps = 10 if dim == 2 else (3 if model == co.SNOW else 6)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, dim, model, res, steps, rebalance, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, migrated = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    x, v = moving_block(dim, res)
+    ref = co.CpuSim(x, model, res, v=v)
+    ref.advance(steps)
+    check(got, ref.particles(), steps, res)
