@@ -40,8 +40,6 @@ struct nmpm_sim {
     size_t n_store = 0;       // slab mode: entries in store[cur] incl. migrated-away ("gone") and just-received ones
     size_t n_gone = 0;        // slab mode: entries of store[cur] whose key is kKeyGone
     bool slab = false;
-    int gx0 = 0, gx1 = 0;     // slab mode: node planes [gx0, gx1+2) are cleared / updated (ownership range, or its union
-                              // with the previous one for the step right after nmpm_slab_set_range)
     MaterialParams P{};
     nmpm_options opt{};
     float E = 0, nu = 0, gravity = 0;
@@ -52,6 +50,14 @@ struct nmpm_sim {
     ParticleStore store[2]{};
     int cur = 0;
     float4* grid = nullptr;
+    // node boxes (GridBox, device): box[box_cur] bounds the particles of the current step, box[(box_cur+2)%3]
+    // the nodes the previous P2G wrote (cleared at the start of the next one), box[(box_cur+1)%3] is being
+    // built by the G2P in flight
+    GridBox* d_box = nullptr;
+    int* d_box_partial = nullptr;  // one partial box (8 ints) per G2P warp
+    int box_cur = 0;
+    std::vector<std::pair<int, int>> dirty_planes;  // slab mode: node planes written by nmpm_grid_add_planes
+    bool box_valid = false;   // box[box_cur] describes store[cur]
     bool grid_valid = false;  // false until the first p2g: the reference's grid() is empty (src/solver.cpp:52-57)
 
     SortWorkspace sort;
@@ -74,6 +80,7 @@ struct nmpm_sim {
     struct StepGraph {
         cudaGraphExec_t exec = nullptr;
         int cur_after = 0;
+        int box_after = 0;
         bool keys_valid_after = false;
         int launches = 0;
     };
@@ -222,7 +229,6 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
             return NMPM_ERR_INVALID;
         }
         if ((size_t) h->opt.capacity > n) h->cap = (size_t) h->opt.capacity;
-        h->gx0 = h->opt.slab_x0, h->gx1 = h->opt.slab_x1;
         h->opt.use_graph = 0;   // particle counts change every step
         h->opt.sort_every = 1;  // migrants are compacted away by the per-step sort
     }
@@ -256,6 +262,10 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
     if (int rc = alloc_store(h, h->store[0])) return rc;
     if (int rc = alloc_store(h, h->store[1])) return rc;
     CUDA_TRY(h, cudaMalloc(&h->grid, h->cells * sizeof(float4)));
+    CUDA_TRY(h, cudaMemset(h->grid, 0, h->cells * sizeof(float4)));  // the only dense clear; afterwards box by box
+    CUDA_TRY(h, cudaMalloc(&h->d_box, 3 * sizeof(GridBox)));
+    CUDA_TRY(h, cudaMalloc(&h->d_box_partial, ((h->cap + 127) / 128 * 4 + 4) * 8 * sizeof(int)));
+    for (int k = 0; k < 3; ++k) k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + k);
     CUDA_TRY(h, cudaMalloc(&h->d_error, sizeof(int)));
     CUDA_TRY(h, cudaMemset(h->d_error, 0, sizeof(int)));
     CUDA_TRY(h, cudaMallocHost(&h->h_error, sizeof(int)));
@@ -303,6 +313,8 @@ void nmpm_destroy(nmpm_handle h) {
     free_store(h->store[0]);
     free_store(h->store[1]);
     if (h->grid) cudaFree(h->grid);
+    if (h->d_box) cudaFree(h->d_box);
+    if (h->d_box_partial) cudaFree(h->d_box_partial);
     if (h->d_error) cudaFree(h->d_error);
     if (h->h_error) cudaFreeHost(h->h_error);
     if (h->staging) cudaFree(h->staging);
@@ -460,9 +472,13 @@ static int do_sort(nmpm_sim* h) {
     const uint32_t n = (uint32_t) h->n_store;
     ParticleStore& S = h->store[h->cur];
     if (!h->keys_valid) {
+        // (first step / after an upload) the key pass also builds the node box of the current positions
+        k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + h->box_cur);
         NMPM_DISPATCH_DIM(h, (k_cell_keys<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(
-                                 S, n, h->P, h->tiles_per_axis, h->sort.keys_a, nullptr, h->d_error)));
-        h->launches++;
+                                 S, n, h->P, h->tiles_per_axis, h->sort.keys_a, nullptr, h->d_error,
+                                 h->d_box + h->box_cur)));
+        h->launches += 2;
+        h->box_valid = true;
     }
     uint32_t *ks = nullptr, *perm = nullptr;
     h->launches += radix_sort_pairs(h->sort, n, h->key_bits, h->stream, &ks, &perm);
@@ -474,24 +490,31 @@ static int do_sort(nmpm_sim* h) {
     return NMPM_OK;
 }
 
-// node range this sim clears and updates: the whole grid, or planes [x0, min(x1+2, n1)) of its slab
-static void grid_range(const nmpm_sim* h, size_t* first, size_t* count) {
-    const size_t plane = h->cells / (size_t) (h->res + 1);
-    if (!h->slab) {
-        *first = 0, *count = h->cells;
-        return;
-    }
-    const int n1 = h->res + 1;
-    const int p0 = h->gx0 < n1 ? h->gx0 : n1;
-    const int p1 = h->gx1 + 2 < n1 ? h->gx1 + 2 : n1;
-    *first = (size_t) p0 * plane;
-    *count = (size_t) (p1 > p0 ? p1 - p0 : 0) * plane;
+constexpr int kBoxBlocks = 148 * 8;  // grid-stride kernels over a node box: 8 CTAs of 256 threads per SM
+
+// make box[box_cur] valid when no key pass ran for the current positions (sort_every == 0 on the first step)
+static int ensure_box(nmpm_sim* h) {
+    if (h->box_valid || h->n_store == 0) return NMPM_OK;
+    const uint32_t n = (uint32_t) h->n_store;
+    k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + h->box_cur);
+    NMPM_DISPATCH_DIM(h, (k_cell_keys<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(
+                             h->store[h->cur], n, h->P, h->tiles_per_axis, h->sort.keys_b, nullptr, h->d_error,
+                             h->d_box + h->box_cur)));
+    h->launches += 2;
+    h->box_valid = true;
+    return NMPM_OK;
 }
 
 static int do_p2g(nmpm_sim* h) {
-    size_t g_first = 0, g_count = 0;
-    grid_range(h, &g_first, &g_count);
-    if (g_count) CUDA_TRY(h, cudaMemsetAsync(h->grid + g_first, 0, g_count * sizeof(float4), h->stream));
+    if (int rc = ensure_box(h)) return rc;
+    // K1: clear what the previous P2G (and, for a slab, the neighbours' ghost planes) wrote
+    NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + (h->box_cur + 2) % 3,
+                                                                            h->P.n1)));
+    h->launches++;
+    for (const auto& pr : h->dirty_planes)
+        CUDA_TRY(h, cudaMemsetAsync(nmpm_grid_plane_ptr(h, pr.first), 0, (size_t) pr.second * nmpm_grid_plane_bytes(h),
+                                    h->stream));
+    h->dirty_planes.clear();
     h->grid_valid = true;
     if (h->n == 0) return NMPM_OK;
     const uint32_t n = (uint32_t) h->n;
@@ -509,10 +532,7 @@ static int do_p2g(nmpm_sim* h) {
 }
 
 static int do_grid_op(nmpm_sim* h) {
-    size_t g_first = 0, g_count = 0;
-    grid_range(h, &g_first, &g_count);
-    if (g_count == 0) return NMPM_OK;
-    NMPM_DISPATCH_DIM(h, (k_grid_op<D><<<blocks_for(g_count, 256), 256, 0, h->stream>>>(h->grid, g_first, g_count, h->P)));
+    NMPM_DISPATCH_DIM(h, (k_grid_op<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + h->box_cur, h->P)));
     h->launches++;
     return NMPM_OK;
 }
@@ -520,6 +540,8 @@ static int do_grid_op(nmpm_sim* h) {
 static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullptr, nullptr, 0, nullptr}) {
     if (h->n == 0) {
         h->n_store = 0;
+        h->box_cur = (h->box_cur + 1) % 3;
+        k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + h->box_cur);
         return NMPM_OK;
     }
     const uint32_t n = (uint32_t) h->n;
@@ -528,9 +550,18 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
     // emit the next step's keys only if the next step sorts
     const bool next_sorts = h->opt.sort_every > 0 && ((h->steps_done + 1) % h->opt.sort_every) == 0;
     uint32_t* keys_out = next_sorts ? h->sort.keys_a : nullptr;
+    const int box_next = (h->box_cur + 1) % 3;
+    k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + box_next);
     NMPM_DISPATCH(h, (k_g2p_gather<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(
-                         S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error, mig)));
-    h->launches++;
+                         S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error, mig,
+                         h->d_box_partial)));
+    {   // warps of the launch above (128-thread CTAs): every one of them wrote a partial box
+        const uint32_t nwarps = blocks_for(n, 128) * 4u - ((blocks_for(n, 128) * 128u - n) / 32u);
+        const unsigned rb = nwarps / 1024 + 1 < 148u ? nwarps / 1024 + 1 : 148u;
+        k_box_reduce<<<rb, 256, 0, h->stream>>>(h->d_box_partial, nwarps, h->d_box + box_next);
+    }
+    h->launches += 3;
+    h->box_cur = box_next;
     if (h->perm) h->cur ^= 1;
     h->perm = nullptr;
     h->keys_valid = next_sorts;
@@ -608,7 +639,10 @@ static int step_once(nmpm_sim* h) {
         return NMPM_OK;
     }
     const int se = h->opt.sort_every;
-    const int key = h->cur | (h->keys_valid ? 2 : 0) | ((se > 0 ? (int) (h->steps_done % se) : 0) << 2);
+    const int box0 = h->box_cur;
+    const bool boxv0 = h->box_valid;
+    const int key = h->cur | (h->keys_valid ? 2 : 0) | (box0 << 2) | (boxv0 ? 16 : 0) |
+                    ((se > 0 ? (int) (h->steps_done % se) : 0) << 5);
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
         if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
@@ -633,11 +667,14 @@ static int step_once(nmpm_sim* h) {
             h->launches = l0;
             h->cur = key & 1;
             h->keys_valid = (key & 2) != 0;
+            h->box_cur = box0;
+            h->box_valid = boxv0;
             h->perm = nullptr;
             return step_once(h);
         }
         sg.cur_after = h->cur;
         sg.keys_valid_after = h->keys_valid;
+        sg.box_after = h->box_cur;
         sg.launches = (int) (h->launches - l0);
         it = h->graphs.emplace(key, sg).first;
         CUDA_TRY(h, cudaGraphLaunch(it->second.exec, h->stream));
@@ -646,6 +683,8 @@ static int step_once(nmpm_sim* h) {
     CUDA_TRY(h, cudaGraphLaunch(it->second.exec, h->stream));
     h->cur = it->second.cur_after;
     h->keys_valid = it->second.keys_valid_after;
+    h->box_cur = it->second.box_after;
+    h->box_valid = true;
     h->perm = nullptr;
     h->grid_valid = true;
     h->steps_done++;
@@ -819,6 +858,7 @@ int nmpm_upload_particles(nmpm_handle h, const float* x, const float* v, const f
     h->cur ^= 1;
     h->phase_next = 0;
     h->keys_valid = false;
+    h->box_valid = false;  // rebuilt by the next key pass; the nodes of the last P2G stay scheduled for clearing
     h->perm = nullptr;
     // the sort cadence restarts so that the next step re-bins the new state
     h->steps_done = 0;
@@ -844,7 +884,7 @@ int nmpm_sort_debug(nmpm_handle h, int32_t* base, uint32_t* keys_unsorted, uint3
     ParticleStore& S = h->store[h->cur];
     int32_t* dbase = (int32_t*) h->staging;
     NMPM_DISPATCH_DIM(h, (k_cell_keys<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(
-                             S, (uint32_t) n, h->P, h->tiles_per_axis, h->sort.keys_a, dbase, h->d_error)));
+                             S, (uint32_t) n, h->P, h->tiles_per_axis, h->sort.keys_a, dbase, h->d_error, nullptr)));
     h->launches++;
     if (base) CUDA_TRY(h, cudaMemcpyAsync(base, dbase, n * D * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     if (keys_unsorted)
@@ -960,6 +1000,7 @@ int nmpm_grid_add_planes(nmpm_handle h, int x_plane, int planes, const void* dev
     k_add_planes<<<blocks_for(count, 256), 256, 0, h->stream>>>((float4*) nmpm_grid_plane_ptr(h, x_plane),
                                                               (const float4*) device_src, count);
     h->launches++;
+    h->dirty_planes.emplace_back(x_plane, planes);  // cleared wholesale at the next step (beyond the node box)
     CUDA_TRY(h, cudaGetLastError());
     return NMPM_OK;
 }
@@ -1007,7 +1048,6 @@ int nmpm_slab_grid_g2p(nmpm_handle h, void* send_left, void* send_right, size_t 
     if (int rc = do_g2p(h, mig)) return rc;
     h->steps_done++;
     h->phase_next = 0;
-    h->gx0 = h->opt.slab_x0, h->gx1 = h->opt.slab_x1;  // every particle now obeys the current ownership range
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaMemcpyAsync(h->h_error, h->d_error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     return NMPM_OK;
@@ -1033,7 +1073,7 @@ int nmpm_slab_unpack(nmpm_handle h, const void* recv_left, size_t n_from_left, c
         if (!cnt[s]) continue;
         NMPM_DISPATCH_DIM(h, (k_unpack_records<D><<<blocks_for(cnt[s], 256), 256, 0, h->stream>>>(
                                  (const float*) src[s], (uint32_t) cnt[s], (uint32_t) h->n_store, T, h->P,
-                                 h->tiles_per_axis, h->sort.keys_a)));
+                                 h->tiles_per_axis, h->sort.keys_a, h->d_box + h->box_cur)));
         h->launches++;
         h->n_store += cnt[s];
     }
@@ -1045,10 +1085,8 @@ int nmpm_slab_unpack(nmpm_handle h, const void* recv_left, size_t n_from_left, c
 int nmpm_slab_set_range(nmpm_handle h, int slab_x0, int slab_x1) {
     if (int rc = slab_check(h, "nmpm_slab_set_range")) return rc;
     if (slab_x0 < 0 || slab_x1 <= slab_x0 || h->phase_next != 0) return NMPM_ERR_INVALID;
-    // particles keep their current owner until the next G2P hands them over: until then the grid
-    // range is the union of the old and the new ownership range
-    h->gx0 = slab_x0 < h->gx0 ? slab_x0 : h->gx0;
-    h->gx1 = slab_x1 > h->gx1 ? slab_x1 : h->gx1;
+    // particles keep their current owner until the next G2P hands them over (the node box follows the
+    // particles, not the ownership range, so nothing else changes)
     h->opt.slab_x0 = slab_x0;
     h->opt.slab_x1 = slab_x1;
     return NMPM_OK;
