@@ -1,0 +1,366 @@
+// nuclear_mpm_solver — the reference's headless solver (src/solver.cpp) on the B200 path.
+//
+// Same flags, defaults, progress messages and on-disk outputs as src/solver.cpp:151-217:
+//   --steps N (1000) --cubes N (1) --cube-res N (25) --dim 2|3 (2) --E f (1000) --nu f (0.3)
+//   --gravity f (-100; the help text says -9.8, Q14) --material-model jelly|snow|liquid (jelly)
+//   --cube<k>-x a --cube<k>-y b   (passed as (min,max) of cube<2>(res,min,max) for BOTH axes, Q15)
+//   --dump    tmp/{step}_{x,v,F,C,Jp,timestep,lame,mass,velocity}.txt under the current directory
+//   --help
+// Snapshot ordering (state BEFORE each step's advance, zero grid at step 0, src/solver.cpp:50-58), the
+// `timestep` rule (:92), the constant-hardening `lame` line (Q13) and the 64-stride grid dump (Q12) are kept.
+// The text is what the reference writes (Eigen default IOFormat via include/nclr.h's operator<<), but each
+// file is written with one buffered stream per step instead of one open/append/close per value
+// (src/solver.cpp:66-73) — files are still opened in append mode like the reference does.
+//
+// Extensions (not in the reference):
+//   --scenes FILE [--out-dir DIR]   dataset generation (BASELINE.json config 5): every non-empty line of FILE
+//                    is the flag list of one scene; all scenes are advanced concurrently on the GPU (one
+//                    simulation and CUDA stream each) and dumped to DIR/scene_<k>/tmp/...
+//   --dump-bin       additionally write tmp/{step}_particles.bin (raw Particle<2> records) per step
+//   --parse-only     print the parsed configuration and exit (used by the CPU tests of the flag rules)
+// dim 3 is accepted like in the reference and, like there, builds an empty simulation and does nothing (Q16).
+#include <array>
+#include <cstdint>
+#include <cstdlib>
+#include <filesystem>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <optional>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "nclr.h"
+
+namespace fs = std::filesystem;
+
+constexpr int kColor = 0xED553B;          // src/solver.cpp:17
+constexpr int kGridResolution = 64;       // src/solver.cpp:20
+constexpr nclr::real kDt = 1e-4;          // src/solver.cpp:23
+
+// ---- argv parsing with the rules of the reference's flags::args (flags/include/flags.h:23-132) ----------
+//  * a token starting with '-' is an option (leading dashes stripped), `--k=v` carries its value;
+//  * a token not starting with '-' is the value of the preceding option (so `--gravity -100` has NO value);
+//  * the first occurrence of a key wins; unparsable or missing values fall back to the default;
+//  * booleans are true when present unless the value is one of 0, n, no, f, false.
+class Args {
+public:
+    explicit Args(const std::vector<std::string> &tokens) {
+        std::string current;
+        bool pending = false;
+        auto flush = [&](const std::optional<std::string> &value) {
+            if (!pending) return;
+            options_.emplace(current, value);  // emplace: the first occurrence wins
+            pending = false;
+        };
+        for (const auto &tok : tokens) {
+            if (tok.empty()) continue;
+            if (tok[0] == '-') {
+                flush(std::nullopt);
+                const auto start = tok.find_first_not_of('-');
+                const std::string name = start == std::string::npos ? std::string() : tok.substr(start);
+                const auto eq = name.find('=');
+                pending = true;
+                if (eq != std::string::npos) {
+                    current = name.substr(0, eq);
+                    flush(name.substr(eq + 1));
+                } else {
+                    current = name;
+                }
+            } else if (pending) {
+                flush(tok);
+            }  // positional arguments are ignored by the solver
+        }
+        flush(std::nullopt);
+    }
+
+    template<class T>
+    std::optional<T> get(const std::string &key) const {
+        const auto it = options_.find(key);
+        if (it == options_.end() || !it->second) return std::nullopt;
+        T value;
+        if (std::istringstream(*it->second) >> value) return value;
+        return std::nullopt;
+    }
+    std::optional<std::string> get_string(const std::string &key) const {
+        const auto it = options_.find(key);
+        if (it == options_.end()) return std::nullopt;
+        return it->second;
+    }
+    bool get_bool(const std::string &key, bool fallback) const {
+        const auto it = options_.find(key);
+        if (it == options_.end()) return fallback;
+        if (!it->second) return true;
+        for (const char *f : {"0", "n", "no", "f", "false"})
+            if (*it->second == f) return false;
+        return true;
+    }
+
+private:
+    std::unordered_map<std::string, std::optional<std::string>> options_;
+};
+
+static void help_msg() {  // src/solver.cpp:25-43, verbatim text
+    std::cout << "Usage: ./nuclear_mpm_solver [OPTIONS] COMMAND [ARGS]..." << std::endl;
+    std::cout << "\tNuclearMPM headless solver" << std::endl;
+    std::cout << "Options:" << std::endl;
+    std::cout << "\t--steps\tINTEGER\t[default:1000]\tThe number of simulation steps" << std::endl;
+    std::cout << "\t--cubes\tINTEGER\t[default:1]\tThe number of cubes to add" << std::endl;
+    std::cout << "\t--cube-res\tINTEGER\t[default:25]\tThe resolution of each cube" << std::endl;
+    std::cout << "\t--dim\tINTEGER\t[default:2]\tThe number of dimensions to run the sim in [2d or 3d only!]"
+              << std::endl;
+    std::cout << "\t--E\tFLOAT\t[default:1000.0]\tThe young's modulus of the shape(s)" << std::endl;
+    std::cout << "\t--nu\tFLOAT\t[default:0.3]\tThe poisson's ratio of the shape(s)" << std::endl;
+    std::cout << "\t--gravity\tFLOAT\t[default:-9.8]\tThe gravitational forces" << std::endl;
+    std::cout << "\t--material-model\t[jelly, snow, liquid]\t[default:jelly]\tThe material model to use" << std::endl;
+    std::cout
+            << "\t--cube[n]-[xyz]\t\tEach cube gets its own position, this _must_ be explicitly set (0.1-0.9 for each)"
+            << std::endl;
+    std::cout << "\t--dump\tDump particle state at each timestep (impacts perforamnce)" << std::endl;
+    std::cout << "\t--help\tShow this message and exit" << std::endl;
+}
+
+struct SceneConfig {
+    int steps = 1000, cubes = 1, cube_res = 25, dim = 2;
+    nclr::real E = 1000.0, nu = 0.3, gravity = -100.0;
+    std::string material = "jelly";
+    nclr::MaterialModel model = nclr::MaterialModel::kJelly;
+    bool dump = false, dump_bin = false, help = false, any_flag = false;
+    std::vector<std::array<nclr::real, 2>> cube_minmax;
+    std::string error;  // non-empty: the reference would exit(EXIT_FAILURE) with this on stderr
+    bool show_help_and_fail = false;
+};
+
+static SceneConfig parse_scene(const Args &args) {
+    SceneConfig c;
+    const auto steps = args.get<int>("steps");
+    const auto cubes = args.get<int>("cubes");
+    const auto cube_res = args.get<int>("cube-res");
+    const auto dim = args.get<int>("dim");
+    const auto E = args.get<nclr::real>("E");
+    const auto nu = args.get<nclr::real>("nu");
+    const auto gravity = args.get<nclr::real>("gravity");
+    const auto material = args.get_string("material-model");
+    c.dump = args.get_bool("dump", false);
+    c.dump_bin = args.get_bool("dump-bin", false);
+    c.help = args.get_bool("help", false);
+    if (material && *material != "jelly" && *material != "snow" && *material != "liquid") {  // src/solver.cpp:164-169
+        c.error = "Invalid Option: " + *material;
+        c.show_help_and_fail = true;
+        return c;
+    }
+    c.any_flag = steps || cubes || cube_res || dim || E || nu || gravity || material;  // src/solver.cpp:171
+    c.steps = steps.value_or(1000);
+    c.cubes = cubes.value_or(1);
+    c.cube_res = cube_res.value_or(25);
+    c.dim = dim.value_or(2);
+    c.E = E.value_or(1000.0);
+    c.nu = nu.value_or(0.3);
+    c.gravity = gravity.value_or(-100.0);
+    c.material = material.value_or("jelly");
+    if (c.material == "snow") c.model = nclr::MaterialModel::kSnow;
+    else if (c.material == "liquid")
+        c.model = nclr::MaterialModel::kLiquid;
+    if (c.dim == 2) {
+        for (int cc = 0; cc < c.cubes; ++cc) {  // src/solver.cpp:133-149
+            const auto a = args.get<nclr::real>("cube" + std::to_string(cc) + "-x");
+            const auto b = args.get<nclr::real>("cube" + std::to_string(cc) + "-y");
+            if (!a || !b) {
+                c.error = "Cube: " + std::to_string(cc) + " is missing coordinates";
+                return c;
+            }
+            c.cube_minmax.push_back({*a, *b});
+        }
+    }
+    return c;
+}
+
+static std::vector<nclr::Particle<2>> generate_cubes(const SceneConfig &c) {
+    std::vector<nclr::Particle<2>> particles;
+    for (const auto &mm : c.cube_minmax)
+        for (const auto &pos : nclr::cube<2>(c.cube_res, mm[0], mm[1])) particles.emplace_back(nclr::Particle<2>(pos, kColor));
+    return particles;
+}
+
+// ---- dump writers: the reference's text, one buffered append-mode stream per file ----------------------
+class StepFiles {
+public:
+    StepFiles(const fs::path &dir, int step) : dir_(dir), prefix_(std::to_string(step) + "_") { fs::create_directories(dir_); }
+    std::ofstream &open(const std::string &name) {
+        streams_.emplace_back(std::make_unique<std::ofstream>(dir_ / (prefix_ + name), std::ios::out | std::ios::app));
+        return *streams_.back();
+    }
+
+private:
+    fs::path dir_;
+    std::string prefix_;
+    std::vector<std::unique_ptr<std::ofstream>> streams_;
+};
+
+static void dump_particles(const fs::path &tmp, int step, const SceneConfig &c, nclr::real mu_0, nclr::real lambda_0,
+                           const std::vector<nclr::Particle<2>> &ps) {
+    StepFiles files(tmp, step);
+    auto &ft = files.open("timestep.txt"), &fx = files.open("x.txt"), &fv = files.open("v.txt"), &fF = files.open("F.txt"),
+         &fC = files.open("C.txt"), &fJ = files.open("Jp.txt"), &fl = files.open("lame.txt");
+    const auto timestep = step > 0 ? kDt * step : kDt;  // src/solver.cpp:92
+    using Sim = nclr::MPMSimulation<2>;
+    const auto e = c.material == "snow" ? Sim::kSnowHardening : c.material == "jelly" ? Sim::kJellyHardening : Sim::kLiquidHardening;
+    const nclr::Vector<nclr::real, 2> lame(mu_0 * e, lambda_0 * e);  // Q13: the constant hardening factors
+    const auto lame_row = lame.transpose();
+    for (const auto &p : ps) {
+        ft << timestep << '\n';
+        fx << p.x << '\n';
+        fv << p.v << '\n';
+        fF << p.F << '\n';
+        fC << p.C << '\n';
+        fJ << p.Jp << '\n';
+        fl << lame_row << '\n';
+    }
+    if (c.dump_bin) {
+        std::ofstream fb(tmp / (std::to_string(step) + "_particles.bin"), std::ios::binary);
+        fb.write(reinterpret_cast<const char *>(ps.data()), std::streamsize(ps.size() * sizeof(nclr::Particle<2>)));
+    }
+}
+
+static void dump_cells(const fs::path &tmp, int step, const std::vector<nclr::Cell<2>> &cells) {
+    StepFiles files(tmp, step);
+    auto &fm = files.open("mass.txt"), &fv = files.open("velocity.txt");
+    for (int ii = 0; ii <= kGridResolution; ++ii)
+        for (int jj = 0; jj <= kGridResolution; ++jj) {
+            // Q12: the reference indexes the 65-stride grid with stride 64 (src/solver.cpp:117,124-125)
+            const auto &cell = cells.at(size_t(ii * kGridResolution + jj));
+            fm << cell.mass << '\n';
+            fv << cell.velocity << '\n';
+        }
+}
+
+struct Scene {
+    SceneConfig cfg;
+    fs::path tmp;
+    std::unique_ptr<nclr::MPMSimulation<2>> sim;
+};
+
+// advances every scene in lockstep: each advance() only enqueues work on that scene's CUDA stream, so the
+// small per-scene kernels of all scenes overlap on the GPU; snapshots synchronise one scene at a time
+static void run_scenes(std::vector<Scene> &scenes) {
+    int max_steps = 0;
+    for (auto &s : scenes) max_steps = std::max(max_steps, s.cfg.steps);
+    std::cout << "Running simulation" << std::endl;
+    for (int step = 0; step < max_steps; ++step) {
+        for (auto &s : scenes) {
+            if (step >= s.cfg.steps || !s.cfg.dump) continue;
+            dump_particles(s.tmp, step, s.cfg, s.sim->mu_0, s.sim->lambda_0, s.sim->particles());
+            if (step > 0) dump_cells(s.tmp, step, s.sim->grid());
+            else
+                dump_cells(s.tmp, step,
+                           std::vector<nclr::Cell<2>>((kGridResolution + 1) * (kGridResolution + 1), nclr::Cell<2>()));
+        }
+        for (auto &s : scenes)
+            if (step < s.cfg.steps) s.sim->advance();
+    }
+    for (auto &s : scenes) s.sim->synchronize();
+    std::cout << "Simulation done" << std::endl;
+}
+
+static std::vector<std::string> split_ws(const std::string &line) {
+    std::istringstream is(line);
+    std::vector<std::string> out;
+    for (std::string t; is >> t;) out.push_back(t);
+    return out;
+}
+
+static void print_config(const SceneConfig &c) {
+    std::cout << "steps=" << c.steps << " cubes=" << c.cubes << " cube_res=" << c.cube_res << " dim=" << c.dim << " E=" << c.E
+              << " nu=" << c.nu << " gravity=" << c.gravity << " material=" << c.material << " dump=" << c.dump
+              << " help=" << c.help << " any=" << c.any_flag;
+    for (const auto &mm : c.cube_minmax) std::cout << " cube=(" << mm[0] << "," << mm[1] << ")";
+    if (!c.error.empty()) std::cout << " error=\"" << c.error << "\"";
+    std::cout << std::endl;
+}
+
+int main(int argc, char **argv) {
+    std::vector<std::string> tokens(argv + 1, argv + argc);
+    const Args args(tokens);
+    const auto scenes_file = args.get_string("scenes");
+    const bool parse_only = args.get_bool("parse-only", false);
+
+    std::vector<Scene> scenes;
+    if (scenes_file && !scenes_file->empty()) {
+        const fs::path out_dir = args.get_string("out-dir").value_or(".");
+        std::ifstream in(*scenes_file);
+        if (!in) {
+            std::cerr << "Cannot open scene list: " << *scenes_file << std::endl;
+            return EXIT_FAILURE;
+        }
+        int k = 0;
+        for (std::string line; std::getline(in, line);) {
+            const auto toks = split_ws(line);
+            if (toks.empty() || toks[0][0] == '#') continue;
+            Scene s;
+            s.cfg = parse_scene(Args(toks));
+            if (!s.cfg.error.empty()) {
+                std::cerr << "scene " << k << ": " << s.cfg.error << std::endl;
+                return EXIT_FAILURE;
+            }
+            if (s.cfg.dim != 2) {
+                std::cerr << "scene " << k << ": only --dim 2 scenes can be batched" << std::endl;
+                return EXIT_FAILURE;
+            }
+            char name[32];
+            std::snprintf(name, sizeof(name), "scene_%04d", k++);
+            s.tmp = out_dir / name / "tmp";
+            scenes.push_back(std::move(s));
+        }
+    } else {
+        Scene s;
+        s.cfg = parse_scene(args);
+        if (parse_only) {
+            print_config(s.cfg);
+            return s.cfg.error.empty() ? EXIT_SUCCESS : EXIT_FAILURE;
+        }
+        if (s.cfg.show_help_and_fail) {
+            std::cerr << s.cfg.error << std::endl;
+            help_msg();
+            return EXIT_FAILURE;
+        }
+        if (s.cfg.help || !s.cfg.any_flag) help_msg();  // the reference prints the help and carries on
+        if (!s.cfg.error.empty()) {
+            std::cerr << s.cfg.error << std::endl;
+            return EXIT_FAILURE;
+        }
+        s.tmp = fs::canonical(".") / "tmp";  // src/solver.cpp:64-67
+        scenes.push_back(std::move(s));
+    }
+    if (parse_only) {
+        for (const auto &s : scenes) print_config(s.cfg);
+        return EXIT_SUCCESS;
+    }
+
+    try {
+        if (scenes.size() == 1 && scenes[0].cfg.dim != 2) {  // Q16: the reference's 3D branch is a no-op
+            const auto &c = scenes[0].cfg;
+            nclr::MPMSimulation<3> sim(std::vector<nclr::Particle<3>>{}, c.model, kGridResolution, kDt, c.E, c.nu, c.gravity);
+            return EXIT_SUCCESS;
+        }
+        for (auto &s : scenes)
+            s.sim = std::make_unique<nclr::MPMSimulation<2>>(generate_cubes(s.cfg), s.cfg.model, kGridResolution, kDt, s.cfg.E,
+                                                             s.cfg.nu, s.cfg.gravity);
+        bool any_dump = false;
+        for (const auto &s : scenes) any_dump = any_dump || s.cfg.dump;
+        run_scenes(scenes);
+        if (any_dump) {  // the reference writes after the run; the messages are kept
+            std::cout << "Saving results" << std::endl << "Done saving" << std::endl;
+            std::cout << "Saving grid states" << std::endl << "Done saving" << std::endl;
+        }
+    } catch (const std::out_of_range &e) {
+        // the reference dies in std::terminate on the uncaught exception of vector::at (Q5)
+        std::cerr << "terminate called after throwing an instance of 'std::out_of_range'\n  what():  " << e.what() << std::endl;
+        return 134;
+    } catch (const std::exception &e) {
+        std::cerr << "nuclear_mpm_solver: " << e.what() << std::endl;
+        return EXIT_FAILURE;
+    }
+    return EXIT_SUCCESS;
+}
