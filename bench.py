@@ -306,7 +306,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="cfg4")
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
-    ap.add_argument("--sort-every", type=int, default=1)
+    ap.add_argument("--sort-every", type=int, default=4)
     ap.add_argument("--p2g-variant", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--rebalance-every", type=int, default=20, help="multi-GPU: re-balance slab boundaries every k steps")

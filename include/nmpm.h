@@ -47,7 +47,8 @@ enum nmpm_phase { NMPM_PHASE_P2G = 0, NMPM_PHASE_GRID_OP = 1, NMPM_PHASE_G2P = 2
 /* tunables that do not change results beyond float summation order */
 typedef struct nmpm_options {
     int device;       /* CUDA device ordinal (default 0) */
-    int sort_every;   /* re-bin + radix-sort particles by cell key every k steps (default 1; 0 = never) */
+    int sort_every;   /* re-bin + radix-sort particles by cell key every k steps (default 4; 0 = never).
+                         Between sorts particles keep their last cell order; only float summation order changes */
     int p2g_variant;  /* 0 = auto, 1 = per-particle float4 REDs, 2 = cell-segmented register accumulation */
     int use_graph;    /* capture the step into a CUDA graph and replay it (default 1) */
     int slab_x0;      /* multi-GPU x-slab: this sim owns particles with slab_x0 <= base.x < slab_x1 */

@@ -7,6 +7,14 @@
 #include "nmpm_math.cuh"
 #include "nmpm_store.cuh"
 
+// occupancy targets (CTAs of 128 threads per SM) of the two particle kernels; see DESIGN.md §5
+#ifndef NMPM_G2P_MINB
+#define NMPM_G2P_MINB 8
+#endif
+#ifndef NMPM_P2G_MINB
+#define NMPM_P2G_MINB 8
+#endif
+
 namespace nmpm {
 
 // Grid node = float4 {momentum/velocity xyz, mass} (2D: {x, y, mass, 0}); dense (res+1)^dim array in
@@ -382,7 +390,7 @@ __device__ __forceinline__ void g2p_update(PState<D>& p, const Mat<D>& Cn, const
 // order without a separate gather pass.  `keys_out` (nullable) receives the NEXT step's cell key of
 // the advected particle, so the next step's sort starts without a key pass.
 template <int D, int MODEL>
-__global__ void __launch_bounds__(128) k_g2p_gather(ParticleStore S, ParticleStore T, const uint32_t* __restrict__ perm,
+__global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore S, ParticleStore T, const uint32_t* __restrict__ perm,
                                                     uint32_t n, MaterialParams P, const float4* __restrict__ grid,
                                                     uint32_t* __restrict__ keys_out, int tiles_per_axis,
                                                     int* __restrict__ error_flag, MigrateArgs mig,

@@ -39,7 +39,7 @@ struct P2GPacket {
 };
 
 template <int D, int MODEL>
-__global__ void __launch_bounds__(kP2GWarps * 32) k_p2g_cell(ParticleStore S, const uint32_t* __restrict__ perm,
+__global__ void __launch_bounds__(kP2GWarps * 32, NMPM_P2G_MINB) k_p2g_cell(ParticleStore S, const uint32_t* __restrict__ perm,
                                                              uint32_t n, MaterialParams P, float4* __restrict__ grid,
                                                              int* __restrict__ error_flag) {
     using PK = P2GPacket<D>;

@@ -159,7 +159,7 @@ class MPMSimulation:
 
     def __init__(self, particles, model, res: int = 64, dt: float = 1e-4, E: float = 1e4, nu: float = 0.2,
                  gravity: float = -100.0, *, v=None, F=None, C=None, Jp=None, mass=None, volume=None,
-                 device: int = 0, sort_every: int = 1, p2g_variant: int = 0, slab=None, capacity: int = 0,
+                 device: int = 0, sort_every: int = 4, p2g_variant: int = 0, slab=None, capacity: int = 0,
                  ids=None):
         self._L = load_library()
         x = _f32(particles)

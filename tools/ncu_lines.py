@@ -65,22 +65,28 @@ for where, n in per_line.most_common(a.top):
 print("--- by opcode")
 for op, n in per_op.most_common(25):
     print(f"{n / tot:7.3%}  {op}")
-print("--- by file / line range")
+print("--- by enclosing function (nmpm_math.cuh) / 20-line block (other files)")
+import bisect
+from pathlib import Path
+math_src = Path(__file__).resolve().parents[1] / "nuclearmpm_b200" / "csrc" / "nmpm_math.cuh"
+starts, names = [], []
+for no, ln in enumerate(math_src.read_text().splitlines(), 1):
+    m = re.match(r"^(?:NMPM_HD|template|#define NMPM_HESTENES_PAIR|#define NMPM_ROT)", ln)
+    m2 = re.search(r"NMPM_HD\s+[\w<>:&\s\*]+?\s(\w+)\(", ln) or re.search(r"#define (NMPM_\w+)", ln)
+    if m2:
+        starts.append(no)
+        names.append(m2.group(1))
 def bucket(where):
     if where is None:
         return "unknown"
     f, l = where
-    if f == "nmpm_math.cuh":
-        for lo, hi, name in ((24, 62, "mat_mul/det/clamp"), (64, 86, "rot/rcp/rsqrt helpers"), (97, 154, "jacobi_pq"),
-                             (165, 254, "jacobi_svd driver+sort"), (258, 293, "nclr_svd/polar"), (304, 311, "hardening"),
-                             (314, 332, "affine_matrix"), (334, 358, "stencil_axis")):
-            if lo <= l <= hi:
-                return f"math:{name}"
+    if f == "nmpm_math.cuh" and starts:
+        k = bisect.bisect_right(starts, l) - 1
+        return "math:" + (names[k] if k >= 0 else "?")
     return f"{f}:{l // 20 * 20}+"
-agg = collections.Counter()
-sagg = collections.Counter()
+agg, sagg = collections.Counter(), collections.Counter()
 for where, n in per_line.items():
     agg[bucket(where)] += n
     sagg[bucket(where)] += samp_line[where]
-for k, n in agg.most_common(30):
+for k, n in agg.most_common(28):
     print(f"{n / tot:7.3%} {sagg[k] / max(1, stot):7.3%}  {k}")
