@@ -113,6 +113,17 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel: str, n_particles: float):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum per particle on the 3D snow scenes), scaled to this launch."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        per_particle = json.loads(p.read_text())["bytes_per_particle"][kernel]
+        return float(per_particle) * float(n_particles)
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------
 # CPU baseline: the reference's own advance() (oracle/_ref, -Ofast build) or the oracle port
 # ----------------------------------------------------------------------------------------------
@@ -243,7 +254,7 @@ def run_gpu(args):
     dom_ms = phases[dom + "_ms"]
     achieved = ab[dom] * n_total / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic(dom, n_total) if dim == 3 else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_particle": ab[dom],
                 "other": {k: {"ms": phases[k + "_ms"],
                               "achieved_GBps": ab[k] * n_total / (phases[k + "_ms"] * 1e-3) / 1e9 if phases[k + "_ms"] > 0 else 0.0}
@@ -284,7 +295,7 @@ def run_gpu(args):
     if args.no_cpu:
         cpu = None
     else:
-        cpu, _ = cpu_reference_rate(args.workload, 2 if n_total > 1_000_000 else 10, 0, budget_s=10.0)
+        cpu, _ = cpu_reference_rate(args.workload, 6 if n_total > 1_000_000 else 20, 0, budget_s=10.0)
 
     line = {
         "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": args.steps,

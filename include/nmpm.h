@@ -171,6 +171,18 @@ int nmpm_slab_unpack(nmpm_handle h, const void *recv_left, size_t n_from_left, c
 int nmpm_slab_set_range(nmpm_handle h, int slab_x0, int slab_x1);
 /* d_hist: device int[res+1], incremented by the number of live particles per base.x */
 int nmpm_slab_histogram(nmpm_handle h, int *d_hist);
+/* Native slab step: the protocol above driven inside the library with NCCL point-to-point calls
+ * (ncclSend/ncclRecv in a group, one 12-int ncclAllGather for the migrant counts and node boxes) on the
+ * sim's stream; ghost planes are exchanged as the in-plane rectangle the neighbouring slabs can touch.
+ * NCCL is taken with dlopen from the libnccl.so.2 already loaded in the process (or `libnccl_path`).
+ *   unique id: 128 bytes from nmpm_nccl_unique_id on rank 0, distributed by the caller;
+ *   bounds: world+1 ownership boundaries (rank r owns bounds[r] <= base.x < bounds[r+1]). */
+int nmpm_nccl_unique_id(void *out128, const char *libnccl_path);
+int nmpm_slab_comm_init(nmpm_handle h, const void *unique_id128, int rank, int world, const int *bounds,
+                        size_t cap_records, const char *libnccl_path);
+int nmpm_slab_step(nmpm_handle h, int nsteps);
+int nmpm_slab_set_bounds(nmpm_handle h, const int *bounds);
+long long nmpm_slab_migrated(nmpm_handle h);
 /* global ids for the slab's particles (host array of n, creation order); particles() of the global
  * simulation is assembled from nmpm_download_particles_slots by scattering on ids */
 int nmpm_set_ids(nmpm_handle h, const uint32_t *ids);

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <array>
 #include <unordered_map>
 #include <vector>
 
@@ -57,6 +58,8 @@ struct nmpm_sim {
     int* d_box_partial = nullptr;  // one partial box (8 ints) per G2P warp
     int box_cur = 0;
     std::vector<std::pair<int, int>> dirty_planes;  // slab mode: node planes written by nmpm_grid_add_planes
+    std::vector<std::array<int, 5>> dirty_rects;    // slab mode: in-plane rectangles written by the native ghost exchange
+    struct nmpm_slab_comm* sc = nullptr;            // native slab step (nmpm_slab_comm.inl)
     bool box_valid = false;   // box[box_cur] describes store[cur]
     bool grid_valid = false;  // false until the first p2g: the reference's grid() is empty (src/solver.cpp:52-57)
 
@@ -94,6 +97,8 @@ struct nmpm_sim {
 
     std::string last_error;
 };
+
+static void slab_comm_free(nmpm_sim* h);
 
 #define CUDA_TRY(h, expr)                                                                              \
     do {                                                                                               \
@@ -230,7 +235,7 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
         }
         if ((size_t) h->opt.capacity > n) h->cap = (size_t) h->opt.capacity;
         h->opt.use_graph = 0;   // particle counts change every step
-        h->opt.sort_every = 1;  // migrants are compacted away by the per-step sort
+        if (h->opt.sort_every < 1) h->opt.sort_every = 1;  // migrants are compacted away by the sorts
     }
     h->E = E, h->nu = nu, h->gravity = gravity;
     h->device = h->opt.device;
@@ -310,6 +315,7 @@ void nmpm_destroy(nmpm_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    slab_comm_free(h);
     free_store(h->store[0]);
     free_store(h->store[1]);
     if (h->grid) cudaFree(h->grid);
@@ -515,17 +521,26 @@ static int do_p2g(nmpm_sim* h) {
         CUDA_TRY(h, cudaMemsetAsync(nmpm_grid_plane_ptr(h, pr.first), 0, (size_t) pr.second * nmpm_grid_plane_bytes(h),
                                     h->stream));
     h->dirty_planes.clear();
+    for (const auto& r : h->dirty_rects) {
+        const size_t nodes = (size_t) 2 * r[2] * r[4];
+        k_rect<2><<<blocks_for(nodes, 256), 256, 0, h->stream>>>(h->grid, nmpm_grid_plane_bytes(h) / sizeof(float4), h->P.n1, r[0],
+                                                                 2, r[1], r[2], r[3], r[4], nullptr);
+        h->launches++;
+    }
+    h->dirty_rects.clear();
     h->grid_valid = true;
     if (h->n == 0) return NMPM_OK;
     const uint32_t n = (uint32_t) h->n;
     ParticleStore& S = h->store[h->cur];
+    // slab mode, step without a sort: slots of migrated-away particles are still in the store
+    const uint32_t* gone_keys = (h->slab && !h->perm && h->n_gone) ? h->sort.keys_a : nullptr;
     int variant = h->opt.p2g_variant;
     if (variant == 0) variant = (h->opt.sort_every > 0) ? 2 : 1;
     if (variant == 2) {
-        NMPM_DISPATCH(h, (launch_p2g_cell<D, MODEL>(S, h->perm, n, h->P, h->grid, h->d_error, h->stream)));
+        NMPM_DISPATCH(h, (launch_p2g_cell<D, MODEL>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
     } else {
         NMPM_DISPATCH(h, (k_p2g_scatter<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, h->perm, n, h->P,
-                                                                                            h->grid, h->d_error)));
+                                                                                            h->grid, h->d_error, gone_keys)));
     }
     h->launches++;
     return NMPM_OK;
@@ -549,12 +564,14 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
     ParticleStore& T = h->perm ? h->store[h->cur ^ 1] : S;
     // emit the next step's keys only if the next step sorts
     const bool next_sorts = h->opt.sort_every > 0 && ((h->steps_done + 1) % h->opt.sort_every) == 0;
-    uint32_t* keys_out = next_sorts ? h->sort.keys_a : nullptr;
+    // a slab keeps the key array aligned with the slots at all times: it carries the "migrated away" marks
+    uint32_t* keys_out = (next_sorts || h->slab) ? h->sort.keys_a : nullptr;
+    const uint32_t* gone_keys = (h->slab && !h->perm && h->n_gone) ? h->sort.keys_a : nullptr;
     const int box_next = (h->box_cur + 1) % 3;
     k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + box_next);
     NMPM_DISPATCH(h, (k_g2p_gather<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(
                          S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error, mig,
-                         h->d_box_partial)));
+                         h->d_box_partial, gone_keys)));
     {   // warps of the launch above (128-thread CTAs): every one of them wrote a partial box
         const uint32_t nwarps = blocks_for(n, 128) * 4u - ((blocks_for(n, 128) * 128u - n) / 32u);
         const unsigned rb = nwarps / 1024 + 1 < 148u ? nwarps / 1024 + 1 : 148u;
@@ -564,8 +581,8 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
     h->box_cur = box_next;
     if (h->perm) h->cur ^= 1;
     h->perm = nullptr;
-    h->keys_valid = next_sorts;
-    h->n_store = h->n;  // the sorted write compacted the store
+    h->keys_valid = next_sorts || h->slab;
+    h->n_store = h->n;  // a sorted write compacted the store; an in-place step keeps its slots (incl. gone ones)
     return NMPM_OK;
 }
 
@@ -1026,8 +1043,16 @@ int nmpm_slab_p2g(nmpm_handle h) {
         h->last_error = "nmpm_slab_p2g: called in the middle of a step";
         return NMPM_ERR_INVALID;
     }
-    if (int rc = do_sort(h)) return rc;
+    if (h->timing) cudaEventRecord(h->ev[0], h->stream);
+    if (h->steps_done % h->opt.sort_every == 0 || !h->keys_valid) {
+        if (int rc = do_sort(h)) return rc;
+    } else {
+        h->perm = nullptr;
+        h->n = h->n_store;  // in place: every slot, the gone ones are skipped on the device
+    }
+    if (h->timing) cudaEventRecord(h->ev[1], h->stream);
     if (int rc = do_p2g(h)) return rc;
+    if (h->timing) cudaEventRecord(h->ev[2], h->stream);
     h->phase_next = 1;
     CUDA_TRY(h, cudaGetLastError());
     return NMPM_OK;
@@ -1042,10 +1067,26 @@ int nmpm_slab_grid_g2p(nmpm_handle h, void* send_left, void* send_right, size_t 
     }
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaMemsetAsync(d_counts, 0, 4 * sizeof(int), h->stream));
+    if (h->timing) cudaEventRecord(h->ev[5], h->stream);
     if (int rc = do_grid_op(h)) return rc;
+    if (h->timing) cudaEventRecord(h->ev[3], h->stream);
     MigrateArgs mig{h->opt.slab_x0, h->opt.slab_x1, (float*) send_left, (float*) send_right, (uint32_t) cap_records,
                     d_counts};
     if (int rc = do_g2p(h, mig)) return rc;
+    if (h->timing) {  // per-phase device times of this slab (the ghost exchange between P2G and grid_op is not included)
+        cudaEventRecord(h->ev[4], h->stream);
+        cudaEventSynchronize(h->ev[4]);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+        h->t_ms[NMPM_T_SORT] += ms;
+        cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
+        h->t_ms[NMPM_T_P2G] += ms;
+        cudaEventElapsedTime(&ms, h->ev[5], h->ev[3]);
+        h->t_ms[NMPM_T_GRID] += ms;
+        cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]);
+        h->t_ms[NMPM_T_G2P] += ms;
+        h->t_steps++;
+    }
     h->steps_done++;
     h->phase_next = 0;
     CUDA_TRY(h, cudaGetLastError());
@@ -1057,7 +1098,7 @@ int nmpm_slab_unpack(nmpm_handle h, const void* recv_left, size_t n_from_left, c
                      size_t n_from_right, size_t n_sent) {
     if (int rc = slab_check(h, "nmpm_slab_unpack")) return rc;
     if ((n_from_left && !recv_left) || (n_from_right && !recv_right) || n_sent > h->n_store) return NMPM_ERR_INVALID;
-    if (h->phase_next != 0 || h->n_gone != 0) {
+    if (h->phase_next != 0) {
         h->last_error = "nmpm_slab_unpack: must follow nmpm_slab_grid_g2p";
         return NMPM_ERR_INVALID;
     }
@@ -1077,7 +1118,7 @@ int nmpm_slab_unpack(nmpm_handle h, const void* recv_left, size_t n_from_left, c
         h->launches++;
         h->n_store += cnt[s];
     }
-    h->n_gone = n_sent;
+    h->n_gone += n_sent;  // they stay in the store (marked in the key array) until the next sort drops them
     CUDA_TRY(h, cudaGetLastError());
     return NMPM_OK;
 }
@@ -1094,14 +1135,15 @@ int nmpm_slab_set_range(nmpm_handle h, int slab_x0, int slab_x1) {
 
 int nmpm_slab_histogram(nmpm_handle h, int* d_hist) {
     if (!h || !d_hist) return NMPM_ERR_INVALID;
-    if (h->n_gone != 0 || h->phase_next != 0) {
-        h->last_error = "nmpm_slab_histogram: call between steps, before nmpm_slab_unpack";
+    if (h->phase_next != 0) {
+        h->last_error = "nmpm_slab_histogram: call between steps";
         return NMPM_ERR_INVALID;
     }
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (h->n_store == 0) return NMPM_OK;
     NMPM_DISPATCH_DIM(h, (k_histogram_x<D><<<blocks_for(h->n_store, 256), 256, 0, h->stream>>>(
-                             h->store[h->cur], (uint32_t) h->n_store, h->P, d_hist)));
+                             h->store[h->cur], (uint32_t) h->n_store, h->P, d_hist,
+                             h->n_gone ? h->sort.keys_a : nullptr)));
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return NMPM_OK;
@@ -1162,3 +1204,5 @@ int nmpm_download_particles_slots(nmpm_handle h, float* x, float* v, float* F, f
 }
 
 }  // extern "C"
+
+#include "nmpm_slab_comm.inl"

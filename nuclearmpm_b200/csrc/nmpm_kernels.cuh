@@ -257,9 +257,10 @@ __device__ __forceinline__ bool stencil_of(const float (&x)[D], const MaterialPa
 template <int D, int MODEL>
 __global__ void __launch_bounds__(128) k_p2g_scatter(ParticleStore S, const uint32_t* __restrict__ perm, uint32_t n,
                                                      MaterialParams P, float4* __restrict__ grid,
-                                                     int* __restrict__ error_flag) {
+                                                     int* __restrict__ error_flag, const uint32_t* __restrict__ gone_keys) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (gone_keys && __ldg(gone_keys + i) == kKeyGone) return;  // slab mode between sorts: migrated away
     PState<D> p;
     load_for_p2g<D>(S, perm ? __ldg(perm + i) : i, p);
     int base[D];
@@ -394,10 +395,20 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
                                                     uint32_t n, MaterialParams P, const float4* __restrict__ grid,
                                                     uint32_t* __restrict__ keys_out, int tiles_per_axis,
                                                     int* __restrict__ error_flag, MigrateArgs mig,
-                                                    int* __restrict__ box_partial) {
+                                                    int* __restrict__ box_partial, const uint32_t* __restrict__ gone_keys) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned live = __ballot_sync(0xffffffffu, i < n);
-    if (i >= n) return;
+    // slab mode between sorts: a slot whose particle migrated away is skipped (its key stays kKeyGone)
+    const bool mine = i < n && !(gone_keys && __ldg(gone_keys + i) == kKeyGone);
+    const unsigned live = __ballot_sync(0xffffffffu, mine);
+    if (live == 0u) {  // nobody here owns a particle: leave an empty partial box (k_box_reduce reads every warp's slot)
+        if ((threadIdx.x & 31) == 0) {
+            int4* out = reinterpret_cast<int4*>(box_partial + (size_t) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8);
+            out[0] = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, (int) 0x80000000);
+            out[1] = make_int4((int) 0x80000000, (int) 0x80000000, 0, 0);
+        }
+        return;
+    }
+    if (!mine) return;
     const uint32_t src = perm ? __ldg(perm + i) : i;
     PState<D> p;
     load_for_g2p<D>(S, src, p);
@@ -506,7 +517,8 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
         if (keys_out) keys_out[i] = key;
 #pragma unroll
         for (int d = 0; d < D; ++d) b[d] = min(max(b[d], 0), P.res - 2);
-        box_partial_write<D>(box_partial, live, b, !gone);
+        // migrants stay in the sender's box: the box table of the slab protocol must cover them until they are unpacked
+        box_partial_write<D>(box_partial, live, b, true);
     }
 }
 
@@ -542,11 +554,34 @@ __global__ void __launch_bounds__(256) k_unpack_records(const float* __restrict_
     box_update<D>(box, b, true);
 }
 
+// sub-rectangle of `planes` consecutive node planes: a = slow in-plane axis (y in 3D, none in 2D),
+// b = fast axis (z in 3D, y in 2D).  mode 0: buf <- grid, 1: grid += buf, 2: grid <- 0
+template <int MODE>
+__global__ void __launch_bounds__(256) k_rect(float4* __restrict__ grid, size_t plane_nodes, int n1, int x_plane, int planes,
+                                              int a0, int na, int b0, int nb, float4* __restrict__ buf) {
+    const uint32_t total = (uint32_t) planes * na * nb;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t q = i / nb, b = i - q * nb;
+        const uint32_t p = q / na, a = q - p * na;
+        float4* g = grid + (size_t) (x_plane + p) * plane_nodes + (size_t) (a0 + a) * n1 + (b0 + b);
+        if (MODE == 0) buf[i] = *g;
+        else if (MODE == 1) {
+            float4 v = *g;
+            const float4 w = buf[i];
+            v.x += w.x, v.y += w.y, v.z += w.z, v.w += w.w;
+            *g = v;
+        } else
+            *g = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
 // live particles per base.x (re-balancing of the slab boundaries)
 template <int D>
-__global__ void __launch_bounds__(256) k_histogram_x(ParticleStore S, uint32_t n, MaterialParams P, int* __restrict__ hist) {
+__global__ void __launch_bounds__(256) k_histogram_x(ParticleStore S, uint32_t n, MaterialParams P, int* __restrict__ hist,
+                                                     const uint32_t* __restrict__ keys) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (keys && keys[i] == kKeyGone) return;  // migrated away: counted by its new owner
     float x[D];
     load_position<D>(S, i, x);
     const Stencil1 s = stencil_axis(x[0], P.inv_dx, P.res);

@@ -41,7 +41,8 @@ struct P2GPacket {
 template <int D, int MODEL>
 __global__ void __launch_bounds__(kP2GWarps * 32, NMPM_P2G_MINB) k_p2g_cell(ParticleStore S, const uint32_t* __restrict__ perm,
                                                              uint32_t n, MaterialParams P, float4* __restrict__ grid,
-                                                             int* __restrict__ error_flag) {
+                                                             int* __restrict__ error_flag,
+                                                             const uint32_t* __restrict__ gone_keys) {
     using PK = P2GPacket<D>;
     constexpr int NODES = (D == 3) ? 27 : 9;
     // pk[warp][q][t] = { val_{2q}(2t), val_{2q}(2t+1), val_{2q+1}(2t), val_{2q+1}(2t+1) }
@@ -72,14 +73,21 @@ __global__ void __launch_bounds__(kP2GWarps * 32, NMPM_P2G_MINB) k_p2g_cell(Part
             float fx[D];
             if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
             const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, p.mass, p.volume, P);
+            // slab mode between sorts: a slot whose particle migrated away scatters exact zeros
+            const bool gone = gone_keys && __ldg(gone_keys + first + lane) == kKeyGone;
+            if (gone) {
+                p.mass = 0.0f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) w[d][0] = w[d][1] = w[d][2] = 0.0f;
+            }
 #pragma unroll
             for (int r = 0; r < D; ++r) {
                 float afx = A(r, 0) * fx[0];
 #pragma unroll
                 for (int k = 1; k < D; ++k) afx = fmaf(A(r, k), fx[k], afx);
-                vals[r] = fmaf(-P.dx, afx, p.v[r] * p.mass);  // b_r
+                vals[r] = gone ? 0.0f : fmaf(-P.dx, afx, p.v[r] * p.mass);  // b_r
 #pragma unroll
-                for (int c = 0; c < D; ++c) vals[D + r * D + c] = P.dx * A(r, c);  // A'_rc (row-major here)
+                for (int c = 0; c < D; ++c) vals[D + r * D + c] = gone ? 0.0f : P.dx * A(r, c);  // A'_rc (row-major here)
             }
             vals[D + D * D] = p.mass;
             nd = base[0] * n1 + base[1];
@@ -184,9 +192,9 @@ __global__ void __launch_bounds__(kP2GWarps * 32, NMPM_P2G_MINB) k_p2g_cell(Part
 
 template <int D, int MODEL>
 inline void launch_p2g_cell(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
-                            float4* grid, int* error_flag, cudaStream_t st) {
+                            float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st) {
     const unsigned blocks = (n + kP2GWarps * 32 - 1) / (kP2GWarps * 32);
-    k_p2g_cell<D, MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag);
+    k_p2g_cell<D, MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
 }
 
 }  // namespace nmpm

@@ -108,6 +108,11 @@ def load_library():
     sig("nmpm_slab_unpack", ci, [vp, vp, sz, vp, sz, sz])
     sig("nmpm_slab_set_range", ci, [vp, ci, ci])
     sig("nmpm_slab_histogram", ci, [vp, vp])
+    sig("nmpm_nccl_unique_id", ci, [vp, ct.c_char_p])
+    sig("nmpm_slab_comm_init", ci, [vp, vp, ci, ci, _i32p, sz, ct.c_char_p])
+    sig("nmpm_slab_step", ci, [vp, ci])
+    sig("nmpm_slab_set_bounds", ci, [vp, _i32p])
+    sig("nmpm_slab_migrated", ct.c_longlong, [vp])
     sig("nmpm_set_ids", ci, [vp, _u32p])
     sig("nmpm_download_particles_slots", ci, [vp] + [_fp] * 5 + [_u32p])
     sig("nmpm_num_slots", sz, [vp])

@@ -83,12 +83,12 @@ class _DevArray:
 class GpuSlabEngine:
     """One x-slab on one GPU (libnmpm.so, nmpm_slab_* of include/nmpm.h)."""
 
-    def __init__(self, x, ids, model, res, dt, E, nu, gravity, slab, capacity, device, **state):
+    def __init__(self, x, ids, model, res, dt, E, nu, gravity, slab, capacity, device, sort_every=4, **state):
         import torch
         self.torch = torch
         self.device = torch.device("cuda", device)
         self.sim = _sim.MPMSimulation(x, model, res, dt, E, nu, gravity, device=device, slab=slab, capacity=capacity,
-                                      ids=ids, **state)
+                                      ids=ids, sort_every=sort_every, **state)
         self.sim.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self._L, self._h = self.sim._L, self.sim._h
         self.dim, self.res = self.sim.dim, res
@@ -125,6 +125,41 @@ class GpuSlabEngine:
     def histogram(self, hist):
         self.sim._check(self._L.nmpm_slab_histogram(self._h, ct.c_void_p(hist.data_ptr())), "nmpm_slab_histogram")
 
+    # -- native step: the same protocol inside libnmpm with NCCL calls on the sim's stream -------------
+    @staticmethod
+    def _libnccl_path() -> bytes:
+        try:
+            import nvidia.nccl
+            from pathlib import Path
+            p = Path(nvidia.nccl.__path__[0]) / "lib" / "libnccl.so.2"
+            return str(p).encode() if p.exists() else b""
+        except Exception:
+            return b""
+
+    def native_init(self, dist, group, rank, world, bounds, cap_records):
+        """Create the library's NCCL communicator: rank 0 makes the unique id, torch.distributed carries it."""
+        torch = self.torch
+        buf = (ct.c_ubyte * 128)()
+        path = self._libnccl_path()
+        if rank == 0:
+            self.sim._check(self._L.nmpm_nccl_unique_id(buf, path), "nmpm_nccl_unique_id")
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=self.device)
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().tolist())
+        b = np.ascontiguousarray(bounds, np.int32)
+        self.sim._check(self._L.nmpm_slab_comm_init(self._h, raw, rank, world, b.ctypes.data_as(_sim._i32p),
+                                                    int(cap_records), path), "nmpm_slab_comm_init")
+
+    def native_step(self, nsteps):
+        self.sim._check(self._L.nmpm_slab_step(self._h, int(nsteps)), "nmpm_slab_step")
+
+    def native_set_bounds(self, bounds):
+        b = np.ascontiguousarray(bounds, np.int32)
+        self.sim._check(self._L.nmpm_slab_set_bounds(self._h, b.ctypes.data_as(_sim._i32p)), "nmpm_slab_set_bounds")
+
+    def native_migrated(self):
+        return int(self._L.nmpm_slab_migrated(self._h))
+
     def num_particles(self):
         return self.sim.num_particles()
 
@@ -151,7 +186,7 @@ class SlabSimulation:
     MIN_WIDTH = 4
 
     def __init__(self, particles, model, res=64, dt=1e-4, E=1e4, nu=0.2, gravity=-100.0, *, group=None, device=0,
-                 engine_factory=None, slack=0.5, rebalance_every=0, max_shift=2, bounds=None, **state):
+                 engine_factory=None, slack=0.5, rebalance_every=0, max_shift=2, bounds=None, native=None, **state):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
@@ -176,6 +211,19 @@ class SlabSimulation:
                               self.capacity, device, **sub)
         e = self.engine
         self.W = e.rec_words
+        self.hist = e.new_buffer(self.n1, "int32") if self.rebalance_every else None
+        self.grid_bounds = list(self.bounds)   # boundaries the particles currently obey (exchange A)
+        self.steps = 0
+        self.migrated = 0
+        # native = the protocol below runs inside libnmpm (NCCL send/recv issued from C++); default whenever the
+        # engine offers it and the group is NCCL.  The Python protocol stays as the reference implementation
+        # (gloo CPU tests, and `native=False` for A/B runs).
+        if native is None:
+            native = hasattr(e, "native_init") and dist.get_backend(group) == "nccl"
+        self.native = bool(native)
+        if self.native:
+            e.native_init(dist, group, self.rank, self.world, self.bounds, self.cap_records)
+            return
         self.buf_from_left = e.new_buffer(2 * e.plane_words)
         self.buf_from_right = e.new_buffer(2 * e.plane_words)
         self.send_left = e.new_buffer(self.cap_records * self.W)
@@ -184,10 +232,6 @@ class SlabSimulation:
         self.recv_right = e.new_buffer(self.cap_records * self.W)
         self.counts = e.new_buffer(4, "int32")
         self.table = e.new_buffer(4 * self.world, "int32")
-        self.hist = e.new_buffer(self.n1, "int32") if self.rebalance_every else None
-        self.grid_bounds = list(self.bounds)   # boundaries the particles currently obey (exchange A)
-        self.steps = 0
-        self.migrated = 0
 
     # rank r owns base.x in [b[r], b[r+1]); the outermost slabs also keep whatever lies beyond the grid
     def _own_range(self, b):
@@ -263,9 +307,14 @@ class SlabSimulation:
         new = limited_shift(self.bounds, target, self.max_shift, self.MIN_WIDTH)
         if new != self.bounds:
             self.bounds = new
-            e.set_range(*self._own_range(new))
+            if self.native:
+                e.native_set_bounds(new)
+            else:
+                e.set_range(*self._own_range(new))
 
     def step(self):
+        if self.native:
+            return self.advance(1)
         e = self.engine
         e.p2g()
         self._exchange_planes()
@@ -277,8 +326,21 @@ class SlabSimulation:
         self._exchange_migrants()
 
     def advance(self, nsteps=1):
-        for _ in range(int(nsteps)):
-            self.step()
+        nsteps = int(nsteps)
+        if not self.native:
+            for _ in range(nsteps):
+                self.step()
+            return
+        while nsteps > 0:  # native: whole runs of steps per call, cut only where a re-balance is due
+            k = nsteps
+            if self.rebalance_every:
+                k = min(k, self.rebalance_every - self.steps % self.rebalance_every)
+            self.engine.native_step(k)
+            self.steps += k
+            nsteps -= k
+            self.migrated = self.engine.native_migrated()
+            if self.rebalance_every and self.steps % self.rebalance_every == 0:
+                self._rebalance()
 
     def synchronize(self):
         self.engine.synchronize()
@@ -347,6 +409,17 @@ def bench_slabs(args, x, model, res, desc, rank, world, local):
     dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     ms = float(tmax[0])
     clocks = clk.summary()
+    # per-phase device times of every slab (separate pass: the events serialise the host)
+    sim.engine.sim.timing_enable(True)
+    sim.engine.sim.timing_read(reset=True)
+    sim.advance(min(args.steps, 10))
+    sync()
+    tm = sim.engine.sim.timing_read(reset=True)
+    sim.engine.sim.timing_enable(False)
+    ph = torch.tensor([tm[k] / max(1, tm["steps"]) for k in ("sort", "p2g", "grid", "g2p")] + [float(sim.num_local())],
+                      device="cuda", dtype=torch.float64)
+    ph_all = [torch.zeros_like(ph) for _ in range(world)]
+    dist.all_gather(ph_all, ph)
     # end-to-end: the same steps including a gather of the positions to the host of every rank
     e2e_steps = max(3, min(args.steps, 10))
     sync()
@@ -377,5 +450,22 @@ def bench_slabs(args, x, model, res, desc, rank, world, local):
                 "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                 "what": "per step: slab advance(1) + download of the rank's particle state to host memory "
                         "(no per-step upload: a slab's particle set changes by migration)"},
-        "roofline": None, "cpu_baseline": None,
+        "roofline": _slab_roofline(ph_all, dim), "cpu_baseline": None,
     }
+
+
+def _slab_roofline(ph_all, dim):
+    """Roofline of the dominant kernel on the slowest slab: algorithmic bytes of that slab's particles over the
+    kernel's mean device time there, against the measured HBM peak of ONE GPU."""
+    from bench import ALGO_BYTES, measured_peak_gbs, ncu_traffic
+    peak, src = measured_peak_gbs()
+    rows = [[float(v) for v in t.tolist()] for t in ph_all]
+    r = max(range(len(rows)), key=lambda i: rows[i][1] + rows[i][3])
+    sort_ms, p2g_ms, grid_ms, g2p_ms, n_local = rows[r]
+    dom = "g2p" if g2p_ms >= p2g_ms else "p2g"
+    dom_ms = g2p_ms if dom == "g2p" else p2g_ms
+    ach = ALGO_BYTES[dim][dom] * n_local / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    return {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": ncu_traffic(dom, n_local), "peak_source": src, "rank": r, "particles_on_rank": int(n_local),
+            "algorithmic_bytes_per_particle": ALGO_BYTES[dim][dom],
+            "phase_ms_per_rank": [dict(sort_ms=a, p2g_ms=b, grid_ms=c, g2p_ms=d, particles=int(e)) for a, b, c, d, e in rows]}

@@ -39,8 +39,9 @@ def check(got, ref, k, res):
     assert np.abs(got["Jp"] - ref["Jp"]).max() <= 1e-4 * k
 
 
+@pytest.mark.parametrize("sort_every", [1, 3])
 @pytest.mark.parametrize("dim,model", [(2, co.SNOW), (3, co.JELLY), (3, co.LIQUID), (3, co.SNOW)])
-def test_two_logical_slabs_on_one_gpu(dim, model):
+def test_two_logical_slabs_on_one_gpu(dim, model, sort_every):
     import torch
     res = 64 if dim == 2 else 32
     steps = 10 if dim == 2 else (3 if model == co.SNOW else 6)
@@ -53,7 +54,7 @@ def test_two_logical_slabs_on_one_gpu(dim, model):
     for (x0, x1) in ranges:
         mine = np.nonzero((bx >= x0) & (bx < x1))[0]
         eng.append(slab.GpuSlabEngine(x[mine], mine.astype(np.uint32), model, res, 1e-4, 1e4, 0.2, -100.0, (x0, x1),
-                                      len(x) + 1024, 0, v=v[mine]))
+                                      len(x) + 1024, 0, v=v[mine], sort_every=sort_every))
     W, cap = eng[0].rec_words, len(x)
     send = [[e.new_buffer(cap * W), e.new_buffer(cap * W)] for e in eng]
     counts = [e.new_buffer(4, "int32") for e in eng]
@@ -103,7 +104,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _nccl_worker(rank, world, port, dim, model, res, steps, rebalance, q):
+def _nccl_worker(rank, world, port, dim, model, res, steps, rebalance, native, q):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -111,7 +112,7 @@ def _nccl_worker(rank, world, port, dim, model, res, steps, rebalance, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         x, v = moving_block(dim, res)
-        sim = slab.SlabSimulation(x, model, res, device=rank, rebalance_every=rebalance, v=v)
+        sim = slab.SlabSimulation(x, model, res, device=rank, rebalance_every=rebalance, native=native, v=v)
         sim.advance(steps)
         out = sim.particles(dst=0)
         if rank == 0:
@@ -120,8 +121,10 @@ def _nccl_worker(rank, world, port, dim, model, res, steps, rebalance, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dim,model,rebalance", [(3, co.JELLY, 0), (3, co.SNOW, 2), (2, co.LIQUID, 3)])
-def test_slab_simulation_over_nccl(dim, model, rebalance):
+@pytest.mark.parametrize("dim,model,rebalance,native", [(3, co.JELLY, 0, True), (3, co.SNOW, 2, True), (2, co.LIQUID, 3, True),
+                                                        (3, co.JELLY, 2, False), (2, co.SNOW, 0, False)])
+def test_slab_simulation_over_nccl(dim, model, rebalance, native):
+    """native=True: the protocol inside libnmpm (ncclSend/ncclRecv from C++); False: slab.py over torch.distributed."""
     import torch
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 4)
@@ -132,13 +135,14 @@ def test_slab_simulation_over_nccl(dim, model, rebalance):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, dim, model, res, steps, rebalance, q)) for r in range(world)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, dim, model, res, steps, rebalance, native, q)) for r in range(world)]
     for p in procs:
         p.start()
     got, migrated = q.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    assert migrated > 0
     x, v = moving_block(dim, res)
     ref = co.CpuSim(x, model, res, v=v)
     ref.advance(steps)

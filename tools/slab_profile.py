@@ -23,7 +23,7 @@ rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 x, model, res, desc = bench.scene(a.workload)
-sim = slab.SlabSimulation(x, model, res, device=local)
+sim = slab.SlabSimulation(x, model, res, device=local, native=False)
 sim.advance(5)
 torch.cuda.synchronize()
 seg = {}
@@ -53,9 +53,21 @@ sim.advance(a.steps)
 torch.cuda.synchronize()
 dist.barrier()
 free = (time.perf_counter() - t0) / a.steps
+# the same steps through the native (in-library NCCL) driver
+del sim
+simn = slab.SlabSimulation(x, model, res, device=local, native=True)
+simn.advance(5)
+torch.cuda.synchronize()
+dist.barrier()
+t0 = time.perf_counter()
+simn.advance(a.steps)
+torch.cuda.synchronize()
+dist.barrier()
+free_native = (time.perf_counter() - t0) / a.steps
+sim = simn
 if rank == 0:
     print(f"{desc}; world {dist.get_world_size()}; local particles {sim.num_local()}")
     for k, (h, g) in seg.items():
         print(f"  {k:40s} host-issue {1e3 * h / a.steps:7.3f} ms   issue+device {1e3 * g / a.steps:7.3f} ms")
-    print(f"  free-running step: {1e3 * free:.3f} ms")
+    print(f"  free-running step: python driver {1e3 * free:.3f} ms, native driver {1e3 * free_native:.3f} ms")
 dist.destroy_process_group()
