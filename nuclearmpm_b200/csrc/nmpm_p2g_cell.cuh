@@ -169,22 +169,22 @@ __global__ void __launch_bounds__(kP2GWarps * 32, NMPM_P2G_MINB) k_p2g_cell(Part
             for (int r = 0; r < D; ++r) acc[r] = ffma2(weight, q[r], acc[r]);
             acc_m = ffma2(weight, mass, acc_m);
         } else {
+            // a segment ends inside this pair: scalar math on the halves of the packed accumulators (no
+            // re-packing of half-zero operand pairs)
             if (nn.x != cur) {
                 flush(cur);
                 cur = nn.x;
             }
-            const float2 wa = make_float2(weight.x, 0.0f);
 #pragma unroll
-            for (int r = 0; r < D; ++r) acc[r] = ffma2(wa, q[r], acc[r]);
-            acc_m = ffma2(wa, mass, acc_m);
+            for (int r = 0; r < D; ++r) acc[r].x = fmaf(weight.x, q[r].x, acc[r].x);
+            acc_m.x = fmaf(weight.x, mass.x, acc_m.x);
             if (nb != cur) {
                 flush(cur);
                 cur = nb;
             }
-            const float2 wb = make_float2(0.0f, weight.y);
 #pragma unroll
-            for (int r = 0; r < D; ++r) acc[r] = ffma2(wb, q[r], acc[r]);
-            acc_m = ffma2(wb, mass, acc_m);
+            for (int r = 0; r < D; ++r) acc[r].y = fmaf(weight.y, q[r].y, acc[r].y);
+            acc_m.y = fmaf(weight.y, mass.y, acc_m.y);
         }
     }
     flush(cur);

@@ -50,8 +50,13 @@ def test_fast_polar_and_snow_projection_match_oracle(hm, name):
     if len(Rm):
         assert np.abs(Rm @ Rm.transpose(0, 2, 1) - np.eye(3)).max() <= 5e-6
         assert (np.linalg.det(Rm) > 0.99).all() or name in ("general", "scaled")  # det R = sign(det A) in general
+    newton, hestenes = divmod(fast, 1000000)
     if name != "liquid_diag":
-        assert fast == n  # the fast path must carry these regimes (rank-1 inputs fall back to the Jacobi SVD)
+        assert newton + hestenes == n  # the fast paths carry these regimes (rank-1 inputs fall back to the Jacobi SVD)
+    if name == "snow_F":
+        assert newton == n  # snow's F is always within Newton's basin (singular values clamped to [0.975, 1.0045])
+    if name in ("jelly_rank2", "step0"):
+        assert newton == 0  # singular input must never pass the Newton acceptance test
 
 
 def test_reference_shaped_svd_matches_golden_bitwise_or_tight(hm):
