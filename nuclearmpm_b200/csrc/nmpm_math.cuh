@@ -537,10 +537,19 @@ struct MaterialParams {
     int res, n1;      // n1 = res+1 nodes per axis
 };
 
-// hardening (src/nclr.h:351-372): snow exp(10(1-Jp)) evaluated in double then narrowed (Q8)
+// hardening (src/nclr.h:351-372).  The reference evaluates the snow factor exp(10(1-Jp)) in double and
+// narrows it to float (Q8).  The device uses the fp32 expf (<= 2 ulp, and the fp32 argument adds
+// <= 1e-7*|10(1-Jp)| <= 4e-7 relative for Jp >= 0.6): the FP64 pipe of this part is slow enough that the
+// double version cost ~7 % of P2G's stall samples (profiles/r01e).  -DNMPM_EXACT_HARDENING restores it.
 template <int MODEL>
 NMPM_HD float hardening_e(float Jp) {
-    if constexpr (MODEL == 0) return (float) exp(10.0 * (1.0 - (double) Jp));
+    if constexpr (MODEL == 0) {
+#ifdef NMPM_EXACT_HARDENING
+        return (float) exp(10.0 * (1.0 - (double) Jp));
+#else
+        return expf(10.0f * (1.0f - Jp));
+#endif
+    }
     if constexpr (MODEL == 1) return 0.3f;
     return 1.0f;
 }

@@ -49,7 +49,7 @@ void hm_svd3(const float* A, float* U, float* S, float* V, long n) {
         for (int k = 0; k < 3; ++k) S[i * 3 + k] = sig[k];
     }
 }
-void hm_affine3(int model, const float* F, const float* C, const float* Jp, float mass, float volume, float mu_0,
+void hm_affine3(int model, const float* F, const float* C, const float* Jp, const float* mass, const float* volume, float mu_0,
                 float lambda_0, float dt, float inv_dx, float* A, long n) {
     MaterialParams P{};
     P.mu_0 = mu_0, P.lambda_0 = lambda_0, P.dt = dt, P.inv_dx = inv_dx, P.dx = 1.0f / inv_dx;
@@ -57,11 +57,11 @@ void hm_affine3(int model, const float* F, const float* C, const float* Jp, floa
     for (long i = 0; i < n; ++i) {
         Mat<3> f, c, a;
         for (int k = 0; k < 9; ++k) f.m[k] = F[i * 9 + k], c.m[k] = C[i * 9 + k];
-        if (model == 0) a = affine_matrix<3, 0>(f, c, Jp[i], mass, volume, P);
+        if (model == 0) a = affine_matrix<3, 0>(f, c, Jp[i], mass[i], volume[i], P);
         else if (model == 1)
-            a = affine_matrix<3, 1>(f, c, Jp[i], mass, volume, P);
+            a = affine_matrix<3, 1>(f, c, Jp[i], mass[i], volume[i], P);
         else
-            a = affine_matrix<3, 2>(f, c, Jp[i], mass, volume, P);
+            a = affine_matrix<3, 2>(f, c, Jp[i], mass[i], volume[i], P);
         for (int k = 0; k < 9; ++k) A[i * 9 + k] = a.m[k];
     }
 }

@@ -25,6 +25,10 @@ def hm(tmp_path_factory):
     L = ct.CDLL(str(out))
     L.hm_polar3.restype = ct.c_long
     L.hm_snow_project3.restype = ct.c_long
+    L.hm_polar3.argtypes = [fp, fp, ct.c_long]
+    L.hm_snow_project3.argtypes = [fp, ct.c_float, ct.c_float, fp, ct.c_long]
+    L.hm_svd3.argtypes = [fp, fp, fp, fp, ct.c_long]
+    L.hm_affine3.argtypes = [ct.c_int, fp, fp, fp, fp, fp] + [ct.c_float] * 4 + [fp, ct.c_long]
     return L
 
 
@@ -71,3 +75,24 @@ def test_reference_shaped_svd_matches_golden_bitwise_or_tight(hm):
         scale = max(1.0, np.abs(a).max())
         assert np.abs((u * s) @ v.T - a).max() <= 3e-6 * scale
         assert np.abs(s - np.diag(g["S"][k].T)).max() <= 3e-6 * scale
+
+
+@pytest.mark.parametrize("scene", ["random_3d_snow", "random_3d_jelly", "random_3d_liquid"])
+def test_affine_matrix_matches_reference_golden(hm, scene):
+    """first_piola_kirchoff_stress + mass*C (src/nclr.h:313-337) as the device computes it (Newton / one-sided
+    Jacobi polar, fp32 hardening exponent) against the value the reference header produced (golden `affine0`)."""
+    g = dict(np.load(ROOT / "tests" / "golden" / f"{scene}.npz"))
+    F, C, Jp = (np.ascontiguousarray(g[k], np.float32) for k in ("F0", "C0", "Jp0"))
+    n = len(Jp)
+    mass, volume = (np.ascontiguousarray(g[k], np.float32) for k in ("mass", "volume"))
+    E, nu, res = float(g["E"]), float(g["nu"]), int(g["res"])
+    mu0 = np.float32(E) / (np.float32(2) * (np.float32(1) + np.float32(nu)))
+    lam0 = np.float32(E) * np.float32(nu) / ((np.float32(1) + np.float32(nu)) * (np.float32(1) - np.float32(2) * np.float32(nu)))
+    dx = np.float32(1.0 / res)
+    A = np.empty_like(F)
+    hm.hm_affine3(int(g["model"]), P(F), P(C), P(Jp), P(mass), P(volume),
+                  ct.c_float(float(mu0)), ct.c_float(float(lam0)), ct.c_float(float(g["dt"])),
+                  ct.c_float(float(np.float32(1) / dx)), P(A), n)
+    ref = g["affine0"]
+    scale = max(1.0, float(np.abs(ref).max()))
+    assert np.abs(A - ref).max() <= 2e-5 * scale, (scene, np.abs(A - ref).max(), scale)
