@@ -353,11 +353,36 @@ extern long nmpm_stat_rot, nmpm_stat_sweep, nmpm_stat_calls;
 #else
 #define NMPM_STAT(x) ((void) 0)
 #endif
+// Packed fp32x2 helpers (FFMA2/FMUL2 on sm_100: two fp32 results per issue slot); plain pairs on the host.
+NMPM_HD float2 f2(float a, float b) { return make_float2(a, b); }
+NMPM_HD float2 f2_fma(float2 a, float2 b, float2 c) {
+#ifdef __CUDA_ARCH__
+    return __ffma2_rn(a, b, c);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+NMPM_HD float2 f2_mul(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    return __fmul2_rn(a, b);
+#else
+    return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+
+// Column j of the working pair (A V, V) as three packed words: (a0,a1) (a2,v0) (v1,v2).  A plane rotation
+// of two columns is then 3 x (FMUL2, FFMA2, FMUL2, FFMA2) = 12 issue slots instead of 24 scalar ones.
+struct HCol {
+    float2 w[3];
+};
+
 #define NMPM_HESTENES_PAIR(P, Q)                                                                    \
     {                                                                                               \
-        const float gam = fmaf(a[P][0], a[Q][0], fmaf(a[P][1], a[Q][1], a[P][2] * a[Q][2]));         \
-        if (gam * gam > kTol2 * (nrm[P] * nrm[Q])) {                                                \
-            rotated = true;                                                                         \
+        const float2 pr = f2_mul(col[P].w[0], col[Q].w[0]);                                         \
+        const float gam = fmaf(col[P].w[1].x, col[Q].w[1].x, pr.x + pr.y);                          \
+        const float gg = gam * gam, nn = fmaxf(nrm[P], floor2) * fmaxf(nrm[Q], floor2);             \
+        if (gg > kTol2 * nn) {                                                                      \
+            excess = fmaxf(excess, fmaf(-kSettle2, nn, gg));                                        \
             NMPM_STAT(nmpm_stat_rot);                                                               \
             const float d = nrm[Q] - nrm[P], g2 = gam + gam;                                        \
             const float r = sqrt_approx(fmaf(d, d, g2 * g2));                                       \
@@ -366,13 +391,11 @@ extern long nmpm_stat_rot, nmpm_stat_sweep, nmpm_stat_calls;
             const float c = rsqrt_nr(fmaf(t, t, 1.0f)), sn = c * t;                                 \
             nrm[P] = fmaf(-t, gam, nrm[P]);                                                         \
             nrm[Q] = fmaf(t, gam, nrm[Q]);                                                          \
+            const float2 c2 = f2(c, c), s2 = f2(sn, sn), ns2 = f2(-sn, -sn);                        \
             _Pragma("unroll") for (int e = 0; e < 3; ++e) {                                         \
-                const float x = a[P][e], y = a[Q][e];                                               \
-                a[P][e] = fmaf(c, x, -sn * y);                                                      \
-                a[Q][e] = fmaf(sn, x, c * y);                                                       \
-                const float vx = v[P][e], vy = v[Q][e];                                             \
-                v[P][e] = fmaf(c, vx, -sn * vy);                                                    \
-                v[Q][e] = fmaf(sn, vx, c * vy);                                                     \
+                const float2 x = col[P].w[e], y = col[Q].w[e];                                      \
+                col[P].w[e] = f2_fma(c2, x, f2_mul(ns2, y));                                        \
+                col[Q].w[e] = f2_fma(s2, x, f2_mul(c2, y));                                         \
             }                                                                                       \
         }                                                                                           \
     }
@@ -381,24 +404,37 @@ template <int MODE>
 NMPM_HD bool svd3_recompose(const Mat<3>& A, float lo, float hi, Mat<3>& G) {
     // |a_p . a_q| <= 4 eps |a_p| |a_q| counts as orthogonal
     constexpr float kTol2 = (4.0f * FLT_EPSILON) * (4.0f * FLT_EPSILON);
-    float a[3][3], v[3][3], nrm[3];  // a[j] = column j of A V,  v[j] = column j of V
+    // a sweep whose largest relative inner product was below 2e-4 leaves all of them below ~4e-8 (cyclic Jacobi
+    // converges quadratically): no further sweep, not even a checking one
+    constexpr float kSettle2 = 2.0e-4f * 2.0e-4f;
+    HCol col[3];
+    float nrm[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-#pragma unroll
-        for (int e = 0; e < 3; ++e) {
-            a[j][e] = A(e, j);
-            v[j][e] = (e == j) ? 1.0f : 0.0f;
-        }
-        nrm[j] = fmaf(a[j][0], a[j][0], fmaf(a[j][1], a[j][1], a[j][2] * a[j][2]));
+        col[j].w[0] = f2(A(0, j), A(1, j));
+        col[j].w[1] = f2(A(2, j), (j == 0) ? 1.0f : 0.0f);
+        col[j].w[2] = f2((j == 1) ? 1.0f : 0.0f, (j == 2) ? 1.0f : 0.0f);
+        nrm[j] = fmaf(A(0, j), A(0, j), fmaf(A(1, j), A(1, j), A(2, j) * A(2, j)));
     }
-    bool rotated = true;
+    // A column that the rotations shrank far below sigma_max carries the absolute rounding noise of the large
+    // ones (~eps sigma_max per entry), so its inner products cannot be driven below ~eps sigma_max |a_q|: norms
+    // enter the test floored at (sigma_max/4)^2-ish.  (Its direction is not used anyway: the smallest column is
+    // completed by a cross product below.)  Without the floor rank-deficient input spins to the sweep cap.
+    const float floor2 = (1.0f / 32.0f) * (nrm[0] + nrm[1] + nrm[2]);
+    float excess = 1.0f;  // > 0: some pair of the last sweep was still far from orthogonal
     NMPM_STAT(nmpm_stat_calls);
-    for (int sweep = 0; sweep < 8 && rotated; ++sweep) {
-        rotated = false;
+    for (int sweep = 0; sweep < 8 && excess > 0.0f; ++sweep) {
+        excess = -1.0f;
         NMPM_STAT(nmpm_stat_sweep);
         NMPM_HESTENES_PAIR(0, 1)
         NMPM_HESTENES_PAIR(0, 2)
         NMPM_HESTENES_PAIR(1, 2)
+    }
+    float a[3][3], v[3][3];  // a[j] = column j of A V (= sigma_j u_j),  v[j] = column j of V
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        a[j][0] = col[j].w[0].x, a[j][1] = col[j].w[0].y, a[j][2] = col[j].w[1].x;
+        v[j][0] = col[j].w[1].y, v[j][1] = col[j].w[2].x, v[j][2] = col[j].w[2].y;
     }
     // squared singular values from the final columns (the running values above only steer the sweeps)
 #pragma unroll
@@ -424,27 +460,32 @@ NMPM_HD bool svd3_recompose(const Mat<3>& A, float lo, float hi, Mat<3>& G) {
         q[e] = (k == 0) ? u[2][e] : (k == 1) ? u[0][e] : u[1][e];
     }
     const float ck[3] = {fmaf(p[1], q[2], -p[2] * q[1]), fmaf(p[2], q[0], -p[0] * q[2]), fmaf(p[0], q[1], -p[1] * q[0])};
-    float f[3];
+    // G = sum_j (f_j u_j) v_j^T, rows 0/1 as one packed pair
+    float2 fu01[3];
+    float fu2[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const bool is_k = (j == k);
         float sg = nrm[j] * inv[j];  // sigma_j >= 0
+        float uj[3] = {u[j][0], u[j][1], u[j][2]};
         if (is_k) {
             sg = fmaf(ck[0], a[j][0], fmaf(ck[1], a[j][1], ck[2] * a[j][2]));  // signed: u_k . (sigma_k u_k)
 #pragma unroll
-            for (int e = 0; e < 3; ++e) u[j][e] = ck[e];
+            for (int e = 0; e < 3; ++e) uj[e] = ck[e];
         }
-        f[j] = (MODE == 0) ? 1.0f : clampf(sg, lo, hi);
+        const float f = (MODE == 0) ? 1.0f : clampf(sg, lo, hi);
+        fu01[j] = f2_mul(f2(f, f), f2(uj[0], uj[1]));
+        fu2[j] = f * uj[2];
     }
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            float acc = (f[0] * u[0][r]) * v[0][c];
-            acc = fmaf(f[1] * u[1][r], v[1][c], acc);
-            acc = fmaf(f[2] * u[2][r], v[2][c], acc);
-            G(r, c) = acc;
-        }
+    for (int c = 0; c < 3; ++c) {
+        float2 g01 = f2_mul(fu01[0], f2(v[0][c], v[0][c]));
+        g01 = f2_fma(fu01[1], f2(v[1][c], v[1][c]), g01);
+        g01 = f2_fma(fu01[2], f2(v[2][c], v[2][c]), g01);
+        G(0, c) = g01.x;
+        G(1, c) = g01.y;
+        G(2, c) = fmaf(fu2[2], v[2][c], fmaf(fu2[1], v[1][c], fu2[0] * v[0][c]));
+    }
     return true;
 }
 

@@ -238,15 +238,26 @@ class MPMSimulation:
     def num_particles(self) -> int:
         return int(self._L.nmpm_num_particles(self._h))
 
-    def particles_slots(self) -> dict:
-        """Slab sims: the live particles in device slot order plus their global ids."""
+    def particles_slots(self, out: dict | None = None, compact: bool = True) -> dict:
+        """Slab sims: the live particles in device slot order plus their global ids.
+
+        `out` (optional): preallocated arrays x,v,F,C,Jp,ids with room for >= nmpm_num_slots entries (e.g. views
+        of pinned host memory, which makes the copy run at PCIe speed); the result then holds views of them.
+        compact=False keeps the slots of particles that have just migrated away (ids == 0xFFFFFFFF)."""
         n, d = int(self._L.nmpm_num_slots(self._h)), self.dim
-        out = dict(x=np.empty((n, d), np.float32), v=np.empty((n, d), np.float32),
-                   F=np.empty((n, d, d), np.float32), C=np.empty((n, d, d), np.float32),
-                   Jp=np.empty((n,), np.float32), ids=np.empty((n,), np.uint32))
+        if out is None:
+            out = dict(x=np.empty((n, d), np.float32), v=np.empty((n, d), np.float32),
+                       F=np.empty((n, d, d), np.float32), C=np.empty((n, d, d), np.float32),
+                       Jp=np.empty((n,), np.float32), ids=np.empty((n,), np.uint32))
+        else:
+            if any(len(out[k]) < n for k in ("x", "v", "F", "C", "Jp", "ids")):
+                raise ValueError(f"particles_slots: preallocated arrays hold fewer than {n} slots")
+            out = {k: out[k][:n] for k in ("x", "v", "F", "C", "Jp", "ids")}
         self._check(self._L.nmpm_download_particles_slots(self._h, *[_p(out[k]) for k in ("x", "v", "F", "C", "Jp")],
                                                           out["ids"].ctypes.data_as(_u32p)),
                     "nmpm_download_particles_slots")
+        if not compact:
+            return out
         live = out["ids"] != 0xFFFFFFFF  # slots of particles that have just migrated away
         return out if live.all() else {k: a[live] for k, a in out.items()}
 
