@@ -535,8 +535,12 @@ static int do_p2g(nmpm_sim* h) {
     // slab mode, step without a sort: slots of migrated-away particles are still in the store
     const uint32_t* gone_keys = (h->slab && !h->perm && h->n_gone) ? h->sort.keys_a : nullptr;
     int variant = h->opt.p2g_variant;
-    if (variant == 0) variant = (h->opt.sort_every > 0) ? 2 : 1;
-    if (variant == 2) {
+    if (variant == 0) variant = (h->opt.sort_every > 0) ? 3 : 1;
+    if (variant == 3) {
+        NMPM_DISPATCH(h, (launch_p2g_cell3<D, MODEL, 6>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
+    } else if (variant == 4) {
+        NMPM_DISPATCH(h, (launch_p2g_cell3<D, MODEL, 8>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
+    } else if (variant == 2) {
         NMPM_DISPATCH(h, (launch_p2g_cell<D, MODEL>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
     } else {
         NMPM_DISPATCH(h, (k_p2g_scatter<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, h->perm, n, h->P,

@@ -543,8 +543,23 @@ NMPM_HD Mat<3> nclr_polar_R(const Mat<3>& m) {
 }
 // snow: U clamp(sigma, lo, hi) V^T of nclr_svd(m)  (src/nclr.h:239-247)
 NMPM_HD Mat<3> snow_project(const Mat<3>& m, float lo, float hi) {
-    Mat<3> G;
-    if (svd3_recompose<1>(m, lo, hi, G)) return G;
+    // The one-sided Jacobi runs on m^T (it orthogonalises the ROWS of m): U f(S) V^T of m^T is the transpose of
+    // that of m, and the det(U) = det(V) = +1 / signed sigma_2 rule is symmetric in U and V.  Snow's
+    // F' = (diag(1,1,0) + dt C) F has two near-orthonormal rows (F is within 2.5 % of a rotation) and an O(dt C)
+    // third one, so F' F'^T is nearly diagonal while F'^T F' is a full rank-2 matrix: 2.0 sweeps / 3.0 rotations
+    // per matrix instead of 3.1 / 6.2 (tools/hestenes_sweeps.cpp), and a warp pays the slowest lane.
+    Mat<3> mt, Gt, G;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) mt(i, j) = m(j, i);
+    if (svd3_recompose<1>(mt, lo, hi, Gt)) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) G(i, j) = Gt(j, i);
+        return G;
+    }
     Mat<3> U, V;
     float sig[3];
     nclr_svd<3>(m, U, sig, V);

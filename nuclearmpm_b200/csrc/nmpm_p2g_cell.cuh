@@ -190,6 +190,183 @@ __global__ void __launch_bounds__(kP2GWarps * 32, NMPM_P2G_MINB) k_p2g_cell(Part
     flush(cur);
 }
 
+// ---- K2 (variant 3, 3D): three particle pairs per warp step, three nodes per lane ---------------
+//
+// Same phase A as above.  Phase B changes the lane <-> work mapping: the 27 active lanes form THREE
+// groups of 9; group g walks its own contiguous third of the warp's 32 cell-sorted slots (pairs
+// [0,6), [6,11), [11,16)), a lane is the (j,k) column of the stencil and owns its three nodes
+// i = 0,1,2 in registers.  Per pair of particles a lane then needs
+//     wyz = wy[j] wz[k];  base_r = b_r + A'_r1 j + A'_r2 k;  val_i = base + i A'_.0;  w_i = wx[i] wyz
+//     acc_i += w_i (val_i, m)                                     -> 28 packed fp32x2 instructions
+// for 3 nodes x 2 particles (4.7 per node-particle instead of 7.5), and the warp retires 6 particles per
+// step of 11 shared-memory loads instead of 2: 66 LDS per 32 particles instead of 176 (the v2 loop was
+// MIO-throttled, profiles/r01d_ncu_summary.md).  A segment (run of particles of one cell) that ends
+// costs three vector reductions per lane, as before one per node.
+template <int MODEL, int MINB>
+__global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell3(ParticleStore S, const uint32_t* __restrict__ perm,
+                                                                            uint32_t n, MaterialParams P, float4* __restrict__ grid,
+                                                                            int* __restrict__ error_flag,
+                                                                            const uint32_t* __restrict__ gone_keys) {
+    constexpr int D = 3;
+    constexpr int NV = 16;   // b(3) m | A' col1(3) col2(3) col0(3) | wx(3)
+    constexpr int NQ4 = 8;   // float4 words per particle PAIR
+    constexpr int WSTRIDE = 34;
+    // pk[warp][q][t] = { val_{2q}(2t), val_{2q}(2t+1), val_{2q+1}(2t), val_{2q+1}(2t+1) }
+    __shared__ float4 pk[kP2GWarps][NQ4][16];
+    __shared__ __align__(8) float wt[kP2GWarps][6][WSTRIDE];  // rows 0..2: wy[j], 3..5: wz[k]; column = slot
+    __shared__ __align__(8) int node0[kP2GWarps][32];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t first = (blockIdx.x * kP2GWarps + warp) * 32u;
+    if (first >= n) return;
+    const int cnt = min(32u, n - first);
+    const int n1 = P.n1;
+
+    // ---- phase A (lane = particle) ----------------------------------------------------------
+    {
+        float vals[NV];
+        float w[D][3];
+        int nd = -1;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) vals[k] = 0.0f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) w[d][0] = w[d][1] = w[d][2] = 0.0f;
+        if (lane < cnt) {
+            PState<D> p;
+            load_for_p2g<D>(S, perm ? __ldg(perm + first + lane) : first + lane, p);
+            int base[D];
+            float fx[D];
+            if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
+            const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, p.mass, p.volume, P);
+            const bool gone = gone_keys && __ldg(gone_keys + first + lane) == kKeyGone;
+            if (gone) {
+                p.mass = 0.0f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) w[d][0] = w[d][1] = w[d][2] = 0.0f;
+            }
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                float afx = A(r, 0) * fx[0];
+#pragma unroll
+                for (int k = 1; k < D; ++k) afx = fmaf(A(r, k), fx[k], afx);
+                vals[r] = gone ? 0.0f : fmaf(-P.dx, afx, p.v[r] * p.mass);  // b_r
+                vals[4 + r] = gone ? 0.0f : P.dx * A(r, 1);
+                vals[7 + r] = gone ? 0.0f : P.dx * A(r, 2);
+                vals[10 + r] = gone ? 0.0f : P.dx * A(r, 0);
+            }
+            vals[3] = p.mass;
+            vals[13] = w[0][0], vals[14] = w[0][1], vals[15] = w[0][2];
+            nd = (base[0] * n1 + base[1]) * n1 + base[2];
+        }
+        float* pkf = reinterpret_cast<float*>(&pk[warp][0][0]);
+        const int t = lane >> 1, h = lane & 1;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) pkf[((k >> 1) * 16 + t) * 4 + (k & 1) * 2 + h] = vals[k];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            wt[warp][i][lane] = w[1][i];
+            wt[warp][3 + i][lane] = w[2][i];
+        }
+        node0[warp][lane] = nd;
+    }
+    __syncwarp();
+
+    // ---- phase B (lane = group g, stencil column (j,k); nodes i = 0,1,2 in registers) ---------
+    if (lane >= 27) return;
+    const int g = lane / 9, jk = lane - 9 * g, j = jk / 3, k = jk - 3 * j;
+    const int t_begin = (g == 0) ? 0 : (g == 1) ? 6 : 11;
+    const int t_end = min((g == 0) ? 6 : (g == 1) ? 11 : 16, (cnt + 1) >> 1);
+    if (t_begin >= t_end) return;
+    const float2 jf = splat2((float) j), kf = splat2((float) k), two = splat2(2.0f);
+    const float* wy = &wt[warp][j][0];
+    const float* wz = &wt[warp][3 + k][0];
+    const int off0 = j * n1 + k, plane = n1 * n1;
+
+    float2 acc[3][D], acc_m[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        acc_m[i] = splat2(0.0f);
+#pragma unroll
+        for (int r = 0; r < D; ++r) acc[i][r] = splat2(0.0f);
+    }
+    int cur = node0[warp][2 * t_begin];
+
+    auto flush = [&](int node) {
+        float4* dst = grid + (size_t) (node + off0);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            red_add_f32x4(dst + (size_t) i * plane,
+                          make_float4(acc[i][0].x + acc[i][0].y, acc[i][1].x + acc[i][1].y, acc[i][2].x + acc[i][2].y,
+                                      acc_m[i].x + acc_m[i].y));
+            acc_m[i] = splat2(0.0f);
+#pragma unroll
+            for (int r = 0; r < D; ++r) acc[i][r] = splat2(0.0f);
+        }
+    };
+
+    for (int t = t_begin; t < t_end; ++t) {
+        int2 nn = *reinterpret_cast<const int2*>(&node0[warp][2 * t]);
+        float2 val[NV];
+#pragma unroll
+        for (int q = 0; q < NQ4; ++q) {
+            const float4 f = pk[warp][q][t];
+            val[2 * q] = make_float2(f.x, f.y);
+            val[2 * q + 1] = make_float2(f.z, f.w);
+        }
+        const float2 wyz = fmul2(*reinterpret_cast<const float2*>(wy + 2 * t), *reinterpret_cast<const float2*>(wz + 2 * t));
+        float2 q[3][D], w[3];
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+            q[0][r] = ffma2(val[7 + r], kf, ffma2(val[4 + r], jf, val[r]));
+            q[1][r] = __fadd2_rn(q[0][r], val[10 + r]);
+            q[2][r] = ffma2(val[10 + r], two, q[0][r]);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) w[i] = fmul2(val[13 + i], wyz);
+        const float2 mass = val[3];
+        if (nn.y < 0) nn.y = nn.x;  // odd tail: the padding slot has zero weight
+        if (nn.x != cur) {          // a new cell starts with this pair
+            flush(cur);
+            cur = nn.x;
+        }
+        if (nn.y == cur) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int r = 0; r < D; ++r) acc[i][r] = ffma2(w[i], q[i][r], acc[i][r]);
+                acc_m[i] = ffma2(w[i], mass, acc_m[i]);
+            }
+        } else {  // the cell changes between the two particles of the pair: scalar halves
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int r = 0; r < D; ++r) acc[i][r].x = fmaf(w[i].x, q[i][r].x, acc[i][r].x);
+                acc_m[i].x = fmaf(w[i].x, mass.x, acc_m[i].x);
+            }
+            flush(cur);
+            cur = nn.y;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int r = 0; r < D; ++r) acc[i][r].y = fmaf(w[i].y, q[i][r].y, acc[i][r].y);
+                acc_m[i].y = fmaf(w[i].y, mass.y, acc_m[i].y);
+            }
+        }
+    }
+    flush(cur);
+}
+
+template <int D, int MODEL, int MINB>
+inline void launch_p2g_cell3(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
+                             float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st) {
+    const unsigned blocks = (n + kP2GWarps * 32 - 1) / (kP2GWarps * 32);
+    if constexpr (D == 3) {
+        k_p2g_cell3<MODEL, MINB><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
+    } else {  // 2D scenes are launch-bound (cfg1: 5 000 particles): the v2 kernel stays
+        k_p2g_cell<D, MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
+    }
+}
+
 template <int D, int MODEL>
 inline void launch_p2g_cell(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
                             float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st) {
