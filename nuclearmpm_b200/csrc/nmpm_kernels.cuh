@@ -20,6 +20,8 @@ namespace nmpm {
 // Grid node = float4 {momentum/velocity xyz, mass} (2D: {x, y, mass, 0}); dense (res+1)^dim array in
 // the reference's index order, x slowest (src/nclr.h:141-142,152).  One float4 per node makes the
 // P2G scatter a single vector reduction (RED.E.ADD.F32x4) and the G2P gather a single LDG.128.
+__device__ __forceinline__ float2 splat2g(float a) { return make_float2(a, a); }
+
 template <int D>
 __device__ __forceinline__ float4 node_pack(const float (&mom)[D], float m) {
     if constexpr (D == 3) return make_float4(mom[0], mom[1], mom[2], m);
@@ -417,42 +419,80 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
     if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
     // Gather with the stencil offsets centred on the middle node:  o = ijk - 1 in {-1,0,+1},
     //   v   = sum w g
-    //   B_c = sum w g o_c                  (adds/subtracts only: the o_c = 0 terms vanish at compile time)
+    //   B_c = sum w g o_c                  (the o_c = 0 terms vanish at compile time)
     //   C   = 4 inv_dx (B - v (fx-1)^T)    == sum 4 inv_dx (w g) (ijk - fx)^T   (src/nclr.h:206,223)
-    // x/y components ride in one packed fp32x2 register pair (FFMA2), z (3D) is scalar.
     const int n1 = P.n1;
-    float2 v01 = make_float2(0.0f, 0.0f), B01[D];
-    float v2 = 0.0f, B2[D];
+    const float four_inv_dx = 4.0f * P.inv_dx;
+    float vn[D];
+    Mat<D> Cn;
+    if constexpr (D == 3) {
+        // Sum factorisation: w = wx_i wy_j wz_k is separable, so the 27-node sums are three nested 3-term
+        // sums — along z per (i,j) row (three adjacent float4 nodes), along y per i, along x — and the weight
+        // products are never formed: 126 packed instructions instead of ~270.  Packed pairs: (x,y) components,
+        // and (plain, z-offset-weighted) sums of the z component, which share their operands.
+        const float4* gp = grid + ((size_t) (base[0] * n1 + base[1]) * n1 + base[2]);
+        const int plane = n1 * n1;
+        const float2 wz0 = splat2g(w[2][0]), wz1 = splat2g(w[2][1]), wz2 = splat2g(w[2][2]), nwz0 = splat2g(-w[2][0]);
+        const float2 wzp0 = make_float2(w[2][0], -w[2][0]), wzp1 = make_float2(w[2][1], 0.0f), wzp2 = wz2;
+        float2 v01, vzBzz, Bz01, By01, Bx01;  // v.xy | (v.z, B_z.z) | B_z.xy | B_y.xy | B_x.xy
+        float Byz, Bxz;
 #pragma unroll
-    for (int c = 0; c < D; ++c) B01[c] = make_float2(0.0f, 0.0f), B2[c] = 0.0f;
-    const float2 plus1 = make_float2(1.0f, 1.0f), minus1 = make_float2(-1.0f, -1.0f);
+        for (int ii = 0; ii < 3; ++ii) {
+            float2 t01, tzz, tz01, ty01;  // sums over (j,k) of this i: t.xy | (t.z, t_z.z) | t_z.xy | t_y.xy
+            float tyz;
 #pragma unroll
-    for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-        for (int jj = 0; jj < 3; ++jj) {
-            if constexpr (D == 3) {
-#pragma unroll
-                for (int kk = 0; kk < 3; ++kk) {
-                    const size_t node = ((size_t) (base[0] + ii) * n1 + (base[1] + jj)) * n1 + (base[2] + kk);
-                    const float4 g = ldg4(grid + node);
-                    const float weight = w[0][ii] * w[1][jj] * w[2][kk];
-                    const float2 wv01 = __fmul2_rn(make_float2(weight, weight), make_float2(g.x, g.y));
-                    const float wv2 = weight * g.z;
-                    v01 = __fadd2_rn(v01, wv01);
-                    v2 += wv2;
-                    const int o[3] = {ii - 1, jj - 1, kk - 1};
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        if (o[c] == 1) {
-                            B01[c] = __ffma2_rn(wv01, plus1, B01[c]);
-                            B2[c] += wv2;
-                        } else if (o[c] == -1) {
-                            B01[c] = __ffma2_rn(wv01, minus1, B01[c]);
-                            B2[c] -= wv2;
-                        }
+            for (int jj = 0; jj < 3; ++jj) {
+                const float4* row = gp + (ii * plane + jj * n1);  // 32-bit offset: < 3 * 513^2
+                const float4 g0 = ldg4(row), g1 = ldg4(row + 1), g2 = ldg4(row + 2);
+                float2 s01 = __fmul2_rn(wz0, make_float2(g0.x, g0.y));
+                s01 = __ffma2_rn(wz1, make_float2(g1.x, g1.y), s01);
+                s01 = __ffma2_rn(wz2, make_float2(g2.x, g2.y), s01);
+                float2 sz01 = __fmul2_rn(wz2, make_float2(g2.x, g2.y));
+                sz01 = __ffma2_rn(nwz0, make_float2(g0.x, g0.y), sz01);
+                float2 szz = __fmul2_rn(wzp0, splat2g(g0.z));  // (sum wz g.z, sum wz o_z g.z)
+                szz = __ffma2_rn(wzp1, splat2g(g1.z), szz);
+                szz = __ffma2_rn(wzp2, splat2g(g2.z), szz);
+                const float2 wy = splat2g(w[1][jj]);
+                if (jj == 0) {
+                    t01 = __fmul2_rn(wy, s01), tzz = __fmul2_rn(wy, szz), tz01 = __fmul2_rn(wy, sz01);
+                    ty01 = __fmul2_rn(splat2g(-w[1][0]), s01);
+                    tyz = -w[1][0] * szz.x;
+                } else {
+                    t01 = __ffma2_rn(wy, s01, t01), tzz = __ffma2_rn(wy, szz, tzz), tz01 = __ffma2_rn(wy, sz01, tz01);
+                    if (jj == 2) {
+                        ty01 = __ffma2_rn(wy, s01, ty01);
+                        tyz = fmaf(w[1][2], szz.x, tyz);
                     }
                 }
+            }
+            const float2 wx = splat2g(w[0][ii]);
+            if (ii == 0) {
+                v01 = __fmul2_rn(wx, t01), vzBzz = __fmul2_rn(wx, tzz), Bz01 = __fmul2_rn(wx, tz01);
+                By01 = __fmul2_rn(wx, ty01), Byz = w[0][0] * tyz;
+                Bx01 = __fmul2_rn(splat2g(-w[0][0]), t01), Bxz = -w[0][0] * tzz.x;
             } else {
+                v01 = __ffma2_rn(wx, t01, v01), vzBzz = __ffma2_rn(wx, tzz, vzBzz), Bz01 = __ffma2_rn(wx, tz01, Bz01);
+                By01 = __ffma2_rn(wx, ty01, By01), Byz = fmaf(w[0][ii], tyz, Byz);
+                if (ii == 2) Bx01 = __ffma2_rn(wx, t01, Bx01), Bxz = fmaf(w[0][2], tzz.x, Bxz);
+            }
+        }
+        vn[0] = v01.x, vn[1] = v01.y, vn[2] = vzBzz.x;
+        const float Bc[3][3] = {{Bx01.x, Bx01.y, Bxz}, {By01.x, By01.y, Byz}, {Bz01.x, Bz01.y, vzBzz.y}};  // Bc[c][r]
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float fc = fx[c] - 1.0f;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) Cn(r, c) = four_inv_dx * fmaf(-vn[r], fc, Bc[c][r]);
+        }
+    } else {
+        float2 v01 = make_float2(0.0f, 0.0f), B01[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) B01[c] = make_float2(0.0f, 0.0f);
+        const float2 plus1 = make_float2(1.0f, 1.0f), minus1 = make_float2(-1.0f, -1.0f);
+#pragma unroll
+        for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) {
                 const size_t node = (size_t) (base[0] + ii) * n1 + (base[1] + jj);
                 const float4 g = ldg4(grid + node);
                 const float weight = w[0][ii] * w[1][jj];
@@ -466,18 +506,13 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
                         B01[c] = __ffma2_rn(wv01, minus1, B01[c]);
                 }
             }
-        }
-    float vn[D];
-    Mat<D> Cn;
-    vn[0] = v01.x, vn[1] = v01.y;
-    if constexpr (D == 3) vn[2] = v2;
-    const float four_inv_dx = 4.0f * P.inv_dx;
+        vn[0] = v01.x, vn[1] = v01.y;
 #pragma unroll
-    for (int c = 0; c < D; ++c) {
-        const float fc = fx[c] - 1.0f;
-        Cn(0, c) = four_inv_dx * fmaf(-vn[0], fc, B01[c].x);
-        Cn(1, c) = four_inv_dx * fmaf(-vn[1], fc, B01[c].y);
-        if constexpr (D == 3) Cn(2, c) = four_inv_dx * fmaf(-vn[2], fc, B2[c]);
+        for (int c = 0; c < D; ++c) {
+            const float fc = fx[c] - 1.0f;
+            Cn(0, c) = four_inv_dx * fmaf(-vn[0], fc, B01[c].x);
+            Cn(1, c) = four_inv_dx * fmaf(-vn[1], fc, B01[c].y);
+        }
     }
     g2p_update<D, MODEL>(p, Cn, vn, P);
     store_state<D>(T, i, p);

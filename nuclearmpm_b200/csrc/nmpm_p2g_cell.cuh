@@ -356,6 +356,132 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell3(ParticleStor
     flush(cur);
 }
 
+// ---- K2 (variant 5, 3D): one particle per group step, lane-specific packets ---------------------
+//
+// ncu on variant 3 (profiles/r01e): the kernel is bound by the L1/shared DATA PIPE (l1tex data-pipe
+// wavefronts 93 % of peak), not by issue slots: a 128-bit shared load costs 4 wavefronts whether or not
+// it is a broadcast, so what matters is the number of BYTES each lane pulls out of shared memory
+// (variant 2: 68 B per lane per particle x 32 lanes; variant 3: 72 B x 27 lanes / 3 groups).
+// Here phase A leaves, per particle, the quantities already specialised per stencil column (j,k):
+//     chunk jk (9x):  { b + A'_.1 j + A'_.2 k  (xyz),  wy[j] wz[k] }        read by ONE lane
+//     chunk 9:        { A'_.0 (xyz), mass }                                  read by the 9 lanes of a group
+//     chunk 10:       { wx[0], wx[1], wx[2], base node }                     read by the 9 lanes of a group
+// so a lane reads 48 B per particle of its group (three LDS.128 = 12 wavefronts per group step instead
+// of 38 per pair step), and the per-lane math drops to 16 instructions per particle for its 3 nodes.
+// Groups walk contiguous thirds of the warp's slots ([0,11) [11,22) [22,32)) one particle at a time: no
+// pair packing, hence no "segment ends inside a pair" path.
+template <int MODEL, int MINB>
+__global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell5(ParticleStore S, const uint32_t* __restrict__ perm,
+                                                                   uint32_t n, MaterialParams P, float4* __restrict__ grid,
+                                                                   int* __restrict__ error_flag,
+                                                                   const uint32_t* __restrict__ gone_keys) {
+    constexpr int D = 3;
+    constexpr int CH = 11;  // float4 chunks per particle; odd stride: conflict-free 128-bit stores (lane = slot)
+    __shared__ float4 pkt[kP2GWarps][32 * CH];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t first = (blockIdx.x * kP2GWarps + warp) * 32u;
+    if (first >= n) return;
+    const int cnt = min(32u, n - first);
+    const int n1 = P.n1;
+
+    // ---- phase A (lane = particle) ----------------------------------------------------------
+    if (lane < cnt) {
+        PState<D> p;
+        load_for_p2g<D>(S, perm ? __ldg(perm + first + lane) : first + lane, p);
+        int base[D];
+        float fx[D], w[D][3];
+        if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
+        const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, p.mass, p.volume, P);
+        // slab mode between sorts: a slot whose particle migrated away scatters exact zeros
+        const bool gone = gone_keys && __ldg(gone_keys + first + lane) == kKeyGone;
+        if (gone) {
+            p.mass = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) w[d][0] = w[d][1] = w[d][2] = 0.0f;
+        }
+        float b[D], c0[D], c1[D], c2[D];
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+            float afx = A(r, 0) * fx[0];
+#pragma unroll
+            for (int k = 1; k < D; ++k) afx = fmaf(A(r, k), fx[k], afx);
+            b[r] = fmaf(-P.dx, afx, p.v[r] * p.mass);  // mass*v + A*((ijk-fx)*dx) = b + (dx*A)*ijk
+            c0[r] = P.dx * A(r, 0), c1[r] = P.dx * A(r, 1), c2[r] = P.dx * A(r, 2);
+        }
+        float4* my = &pkt[warp][lane * CH];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float tj[D];
+#pragma unroll
+            for (int r = 0; r < D; ++r) tj[r] = (j == 0) ? b[r] : (j == 1) ? b[r] + c1[r] : fmaf(c1[r], 2.0f, b[r]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float q[D];
+#pragma unroll
+                for (int r = 0; r < D; ++r) q[r] = (k == 0) ? tj[r] : (k == 1) ? tj[r] + c2[r] : fmaf(c2[r], 2.0f, tj[r]);
+                my[j * 3 + k] = make_float4(q[0], q[1], q[2], w[1][j] * w[2][k]);
+            }
+        }
+        my[9] = make_float4(c0[0], c0[1], c0[2], p.mass);
+        my[10] = make_float4(w[0][0], w[0][1], w[0][2], __int_as_float((base[0] * n1 + base[1]) * n1 + base[2]));
+    }
+    __syncwarp();
+
+    // ---- phase B (lane = group g, stencil column (j,k); nodes i = 0,1,2 in registers) ---------
+    if (lane >= 27) return;
+    const int g = lane / 9, jk = lane - 9 * g, j = jk / 3, k = jk - 3 * j;
+    const int s_begin = 11 * g;
+    const int s_end = min((g == 2) ? 32 : s_begin + 11, cnt);
+    if (s_begin >= s_end) return;
+    const int plane = n1 * n1;
+    float4* const gcol = grid + (j * n1 + k);  // this lane's column of the stencil, relative to the base node
+
+    float2 acc01[3];
+    float acc2[3], accm[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
+
+    auto flush = [&](int node) {
+        float4* dst = gcol + node;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            red_add_f32x4(dst + i * plane, make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]));
+            acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
+        }
+    };
+
+    const float4* pp = &pkt[warp][s_begin * CH];
+    int cur = __float_as_int(pp[10].w);
+    for (int s = s_begin; s < s_end; ++s, pp += CH) {
+        const float4 a = pp[jk], c = pp[9], x = pp[10];
+        const int node = __float_as_int(x.w);
+        if (node != cur) {  // a new cell starts: one vector reduction per owned node
+            flush(cur);
+            cur = node;
+        }
+        const float w0 = x.x * a.w, w1 = x.y * a.w, w2 = x.z * a.w;
+        const float2 q0 = make_float2(a.x, a.y), c01 = make_float2(c.x, c.y);
+        const float2 q1 = __fadd2_rn(q0, c01), q2 = ffma2(c01, splat2(2.0f), q0);
+        const float z1 = a.z + c.z, z2 = fmaf(c.z, 2.0f, a.z);
+        acc01[0] = ffma2(splat2(w0), q0, acc01[0]), acc2[0] = fmaf(w0, a.z, acc2[0]), accm[0] = fmaf(w0, c.w, accm[0]);
+        acc01[1] = ffma2(splat2(w1), q1, acc01[1]), acc2[1] = fmaf(w1, z1, acc2[1]), accm[1] = fmaf(w1, c.w, accm[1]);
+        acc01[2] = ffma2(splat2(w2), q2, acc01[2]), acc2[2] = fmaf(w2, z2, acc2[2]), accm[2] = fmaf(w2, c.w, accm[2]);
+    }
+    flush(cur);
+}
+
+template <int D, int MODEL, int MINB>
+inline void launch_p2g_cell5(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
+                             float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st) {
+    const unsigned blocks = (n + kP2GWarps * 32 - 1) / (kP2GWarps * 32);
+    if constexpr (D == 3) {
+        k_p2g_cell5<MODEL, MINB><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
+    } else {
+        k_p2g_cell<D, MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
+    }
+}
+
 template <int D, int MODEL, int MINB>
 inline void launch_p2g_cell3(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
                              float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st) {
