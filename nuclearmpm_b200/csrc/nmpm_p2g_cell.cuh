@@ -471,6 +471,148 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell5(ParticleStor
     flush(cur);
 }
 
+// ---- K2 (variant 7, 3D): variant 5 with three particle STREAMS per warp -------------------------
+//
+// A vector reduction costs the SM ~1.3 cycles per LANE (REDG, B300_MICROARCH.md "Atomics"), so the 27
+// lane-reductions of one flushed cell run cost as much as 35 ordinary instructions, and in variants
+// 3-6 every warp pays three extra flushes because its 32 slots are cut into three group ranges.
+// Here a warp owns 32*C consecutive slots, cut ONCE into three contiguous streams of 11C, 11C and 10C
+// slots.  Per chunk, lanes [0,11) [11,22) [22,32) load the next 11/11/10 particles of streams 0/1/2
+// (phase A), then group g walks them (phase B) with its run accumulators carried from chunk to chunk:
+// the only flushes left are real cell changes plus three per warp, i.e. 3/C per 32 particles.
+template <int MODEL, int MINB>
+__global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell7(ParticleStore S, const uint32_t* __restrict__ perm,
+                                                                   uint32_t n, MaterialParams P, float4* __restrict__ grid,
+                                                                   int* __restrict__ error_flag,
+                                                                   const uint32_t* __restrict__ gone_keys, int chunks) {
+    constexpr int D = 3;
+    constexpr int CH = 11;  // float4 chunks per particle (see variant 5)
+    __shared__ float4 pkt[kP2GWarps][32 * CH];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t per_warp = 32u * (uint32_t) chunks;
+    const uint32_t first = (blockIdx.x * kP2GWarps + warp) * per_warp;
+    if (first >= n) return;
+    const int total = (int) min(per_warp, n - first);
+    const int n1 = P.n1;
+
+    // phase A role: lane -> (stream, index in the stream's slice of this chunk)
+    const int ga = (lane < 11) ? 0 : (lane < 22) ? 1 : 2;
+    const int ia = lane - 11 * ga;
+    const int wa = (ga == 2) ? 10 : 11;                            // particles of stream ga per chunk
+    const int off_a = 11 * ga * chunks;                            // stream start: 0, 11C, 22C
+    const int len_a = max(0, min(wa * chunks, total - off_a));     // stream length (short in the last warp)
+    // phase B role: lane -> (stream, stencil column)
+    const int g = lane / 9, jk = lane - 9 * g, j = jk / 3, k = jk - 3 * j;
+    const int wb = (g == 2) ? 10 : 11;
+    const int len_b = (lane < 27) ? max(0, min(wb * chunks, total - 11 * g * chunks)) : 0;
+    const int plane = n1 * n1;
+    float4* const gcol = grid + (j * n1 + k);
+
+    float2 acc01[3];
+    float acc2[3], accm[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
+    int cur = -1;
+
+    auto flush = [&](int node) {
+        float4* dst = gcol + node;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            red_add_f32x4(dst + i * plane, make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]));
+            acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
+        }
+    };
+
+    for (int c = 0; c < chunks; ++c) {
+        // ---- phase A (lane = particle of stream ga) ------------------------------------------
+        const int pos = c * wa + ia;
+        if (pos < len_a) {
+            const uint32_t slot = first + (uint32_t) (off_a + pos);
+            PState<D> p;
+            load_for_p2g<D>(S, perm ? __ldg(perm + slot) : slot, p);
+            int base[D];
+            float fx[D], w[D][3];
+            if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
+            const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, p.mass, p.volume, P);
+            const bool gone = gone_keys && __ldg(gone_keys + slot) == kKeyGone;
+            if (gone) {  // slab mode between sorts: a slot whose particle migrated away scatters exact zeros
+                p.mass = 0.0f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) w[d][0] = w[d][1] = w[d][2] = 0.0f;
+            }
+            float b[D], c0[D], c1[D], c2[D];
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                float afx = A(r, 0) * fx[0];
+#pragma unroll
+                for (int q = 1; q < D; ++q) afx = fmaf(A(r, q), fx[q], afx);
+                b[r] = fmaf(-P.dx, afx, p.v[r] * p.mass);
+                c0[r] = P.dx * A(r, 0), c1[r] = P.dx * A(r, 1), c2[r] = P.dx * A(r, 2);
+            }
+            float4* my = &pkt[warp][lane * CH];
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) {
+                float tj[D];
+#pragma unroll
+                for (int r = 0; r < D; ++r) tj[r] = (jj == 0) ? b[r] : (jj == 1) ? b[r] + c1[r] : fmaf(c1[r], 2.0f, b[r]);
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) {
+                    float q[D];
+#pragma unroll
+                    for (int r = 0; r < D; ++r) q[r] = (kk == 0) ? tj[r] : (kk == 1) ? tj[r] + c2[r] : fmaf(c2[r], 2.0f, tj[r]);
+                    my[jj * 3 + kk] = make_float4(q[0], q[1], q[2], w[1][jj] * w[2][kk]);
+                }
+            }
+            my[9] = make_float4(c0[0], c0[1], c0[2], p.mass);
+            my[10] = make_float4(w[0][0], w[0][1], w[0][2], __int_as_float((base[0] * n1 + base[1]) * n1 + base[2]));
+        }
+        __syncwarp();
+
+        // ---- phase B (lane = stream g, stencil column (j,k); nodes i = 0,1,2 in registers) -----
+        const int cnt_b = min(wb, len_b - c * wb);  // <= 0 for lanes >= 27 and for exhausted streams
+        const float4* pp = &pkt[warp][(11 * g) * CH];
+        for (int u = 0; u < cnt_b; ++u, pp += CH) {
+            const float4 a = pp[jk], cc = pp[9], x = pp[10];
+            const int node = __float_as_int(x.w);
+            if (node != cur) {  // a new cell starts: one vector reduction per owned node
+                if (cur >= 0) flush(cur);
+                cur = node;
+            }
+            const float w0 = x.x * a.w, w1 = x.y * a.w, w2 = x.z * a.w;
+            const float2 q0 = make_float2(a.x, a.y), c01 = make_float2(cc.x, cc.y);
+            const float2 q1 = __fadd2_rn(q0, c01), q2 = ffma2(c01, splat2(2.0f), q0);
+            const float z1 = a.z + cc.z, z2 = fmaf(cc.z, 2.0f, a.z);
+            acc01[0] = ffma2(splat2(w0), q0, acc01[0]), acc2[0] = fmaf(w0, a.z, acc2[0]), accm[0] = fmaf(w0, cc.w, accm[0]);
+            acc01[1] = ffma2(splat2(w1), q1, acc01[1]), acc2[1] = fmaf(w1, z1, acc2[1]), accm[1] = fmaf(w1, cc.w, accm[1]);
+            acc01[2] = ffma2(splat2(w2), q2, acc01[2]), acc2[2] = fmaf(w2, z2, acc2[2]), accm[2] = fmaf(w2, cc.w, accm[2]);
+        }
+        __syncwarp();  // the packets are overwritten by the next chunk
+    }
+    if (cur >= 0) flush(cur);
+}
+
+// particles per warp = 32 * chunks; fewer chunks on small scenes so that the grid still fills the GPU
+inline int p2g_stream_chunks(uint32_t n) {
+    const uint32_t per_wave = 148u * 6u * kP2GWarps * 32u;  // slots of one resident wave at chunks = 1
+    const uint32_t c = n / (2u * per_wave);
+    return (int) (c < 1u ? 1u : (c > 4u ? 4u : c));
+}
+
+template <int D, int MODEL, int MINB>
+inline void launch_p2g_cell7(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
+                             float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st, int chunks = 0) {
+    if constexpr (D == 3) {
+        if (chunks <= 0) chunks = p2g_stream_chunks(n);
+        const unsigned per_block = kP2GWarps * 32 * chunks;
+        const unsigned blocks = (n + per_block - 1) / per_block;
+        k_p2g_cell7<MODEL, MINB><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys, chunks);
+    } else {
+        const unsigned blocks = (n + kP2GWarps * 32 - 1) / (kP2GWarps * 32);
+        k_p2g_cell<D, MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
+    }
+}
+
 template <int D, int MODEL, int MINB>
 inline void launch_p2g_cell5(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
                              float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st) {
