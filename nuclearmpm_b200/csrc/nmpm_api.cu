@@ -538,6 +538,11 @@ static int do_p2g(nmpm_sim* h) {
     if (variant == 0) variant = (h->opt.sort_every > 0) ? 3 : 1;
     if (variant == 3) {
         NMPM_DISPATCH(h, (launch_p2g_cell3<D, MODEL, 6>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
+    } else if (variant == 8) {
+        NMPM_DISPATCH(h, (launch_p2g_cell8<D, MODEL, 6>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
+    } else if (variant >= 800 && variant < 900) {  // experiments: 8CC = CC chunks per warp
+        NMPM_DISPATCH(h, (launch_p2g_cell8<D, MODEL, 6>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream,
+                                                        variant - 800)));
     } else if (variant == 7) {
         NMPM_DISPATCH(h, (launch_p2g_cell7<D, MODEL, 6>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
     } else if (variant >= 70 && variant < 80) {  // experiments: 7C = C chunks per warp
