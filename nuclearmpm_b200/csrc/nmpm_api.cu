@@ -535,14 +535,11 @@ static int do_p2g(nmpm_sim* h) {
     // slab mode, step without a sort: slots of migrated-away particles are still in the store
     const uint32_t* gone_keys = (h->slab && !h->perm && h->n_gone) ? h->sort.keys_a : nullptr;
     int variant = h->opt.p2g_variant;
-    if (variant == 0) variant = (h->opt.sort_every > 0) ? 3 : 1;
+    // auto: per-particle reductions without binning; with binning the per-column-packet kernel, on three streams per
+    // warp once the scene is large enough for the reductions to miss L2 (measured: profiles/r01g)
+    if (variant == 0) variant = (h->opt.sort_every > 0) ? ((h->dim == 3 && h->n >= ((size_t) 8 << 20)) ? 7 : 6) : 1;
     if (variant == 3) {
         NMPM_DISPATCH(h, (launch_p2g_cell3<D, MODEL, 6>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
-    } else if (variant == 8) {
-        NMPM_DISPATCH(h, (launch_p2g_cell8<D, MODEL, 6>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
-    } else if (variant >= 800 && variant < 900) {  // experiments: 8CC = CC chunks per warp
-        NMPM_DISPATCH(h, (launch_p2g_cell8<D, MODEL, 6>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream,
-                                                        variant - 800)));
     } else if (variant == 7) {
         NMPM_DISPATCH(h, (launch_p2g_cell7<D, MODEL, 6>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
     } else if (variant >= 70 && variant < 80) {  // experiments: 7C = C chunks per warp

@@ -592,209 +592,6 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell7(ParticleStor
     if (cur >= 0) flush(cur);
 }
 
-// ---- K2 (variant 8, 3D): variant 5 + a warp-private node window in shared memory -----------------
-//
-// The reductions are the largest single cost of the cell-segmented kernels: REDG costs the SM's LSU
-// ~1.3 cycles per lane, i.e. 35 cycles per flushed cell run (27 lanes), and between two re-binnings a
-// warp meets ~9 runs per 32 particles (profiles/r01e-g).  Here a warp owns 32*C consecutive slots and a
-// 6x6x6-node window of shared memory anchored at the 4x4x4-cell tile that holds the majority of the
-// current chunk's particles (slots are ordered by tile-blocked keys, so that tile changes about once
-// per 512 slots).  A finished run is ADDED INTO THE WINDOW (three 128-bit load/add/store per lane:
-// 12 LSU wavefronts for the 9 lanes of a group) unless its cell lies outside the tile (a particle that
-// drifted since the last sort), in which case it is reduced to the grid as before.  The window goes to
-// the grid with one vector reduction per touched node when the anchor moves and at the end of the warp.
-// The three groups share the window, so their read-modify-writes are serialised (ballot + one pass per
-// flushing group); a pass touches 27 distinct nodes.  Floating-point sums stay order-dependent only
-// through the final reductions, exactly like the other variants.
-constexpr int kWinN = 6, kWinNodes = kWinN * kWinN * kWinN;
-constexpr int kTileMask3 = 3 | (3 << 10) | (3 << 20);  // low two bits of each 10-bit packed cell coordinate
-
-template <int MODEL, int MINB>
-__global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell8(ParticleStore S, const uint32_t* __restrict__ perm,
-                                                                   uint32_t n, MaterialParams P, float4* __restrict__ grid,
-                                                                   int* __restrict__ error_flag,
-                                                                   const uint32_t* __restrict__ gone_keys, int chunks) {
-    constexpr int D = 3;
-    constexpr int CH = 11;  // float4 chunks per particle (see variant 5)
-    __shared__ float4 pkt[kP2GWarps][32 * CH];
-    __shared__ float4 win[kP2GWarps][kWinNodes];
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t per_warp = 32u * (uint32_t) chunks;
-    const uint32_t first = (blockIdx.x * kP2GWarps + warp) * per_warp;
-    if (first >= n) return;
-    const int total = (int) min(per_warp, n - first);
-    const int n1 = P.n1;
-    float4* const mywin = &win[warp][0];
-    for (int idx = lane; idx < kWinNodes; idx += 32) mywin[idx] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-
-    // phase B role
-    const bool worker = lane < 27;
-    const int g = lane / 9, jk = lane - 9 * g, j = jk / 3, k = jk - 3 * j;
-    const int plane = n1 * n1;
-
-    float2 acc01[3];
-    float acc2[3], accm[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
-    int cur = -1;     // packed base cell (x | y << 10 | z << 20) of the run being accumulated; -1: none
-    int anchor = -1;  // packed origin cell of the window's tile; -1: none
-
-    // run accumulators -> window (cell inside the anchored tile) or -> grid
-    auto flush_acc = [&](int cell) {
-        if (anchor >= 0 && (cell & ~kTileMask3) == anchor) {
-            const int lx = cell & 3, ly = (cell >> 10) & 3, lz = (cell >> 20) & 3;
-            float4* w = mywin + ((lx * kWinN + ly + j) * kWinN + lz + k);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                float4 v = w[i * kWinN * kWinN];
-                v.x += acc01[i].x, v.y += acc01[i].y, v.z += acc2[i], v.w += accm[i];
-                w[i * kWinN * kWinN] = v;
-            }
-        } else {
-            const int bx = cell & 1023, by = (cell >> 10) & 1023, bz = cell >> 20;
-            float4* dst = grid + ((bx * n1 + by + j) * n1 + bz + k);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) red_add_f32x4(dst + i * plane, make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]));
-        }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
-    };
-    // window -> grid (all 32 lanes), leaves the window zeroed
-    auto window_flush = [&]() {
-        const int ox = anchor & 1023, oy = (anchor >> 10) & 1023, oz = anchor >> 20;
-        for (int idx = lane; idx < kWinNodes; idx += 32) {
-            const float4 v = mywin[idx];
-            if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) {
-                const int ix = idx / (kWinN * kWinN), r = idx - ix * (kWinN * kWinN), iy = r / kWinN, iz = r - iy * kWinN;
-                red_add_f32x4(grid + (((ox + ix) * n1 + oy + iy) * n1 + oz + iz), v);
-                mywin[idx] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            }
-        }
-    };
-    __syncwarp();
-
-    for (int c = 0; c < chunks; ++c) {
-        const int cnt = min(32, total - 32 * c);
-        if (cnt <= 0) break;
-        // ---- phase A (lane = particle) ------------------------------------------------------
-        int cell = -1;
-        if (lane < cnt) {
-            const uint32_t slot = first + (uint32_t) (32 * c + lane);
-            PState<D> p;
-            load_for_p2g<D>(S, perm ? __ldg(perm + slot) : slot, p);
-            int base[D];
-            float fx[D], w[D][3];
-            if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
-            const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, p.mass, p.volume, P);
-            const bool gone = gone_keys && __ldg(gone_keys + slot) == kKeyGone;
-            if (gone) {  // slab mode between sorts: a slot whose particle migrated away scatters exact zeros
-                p.mass = 0.0f;
-#pragma unroll
-                for (int d = 0; d < D; ++d) w[d][0] = w[d][1] = w[d][2] = 0.0f;
-            }
-            float b[D], c0[D], c1[D], c2[D];
-#pragma unroll
-            for (int r = 0; r < D; ++r) {
-                float afx = A(r, 0) * fx[0];
-#pragma unroll
-                for (int q = 1; q < D; ++q) afx = fmaf(A(r, q), fx[q], afx);
-                b[r] = fmaf(-P.dx, afx, p.v[r] * p.mass);
-                c0[r] = P.dx * A(r, 0), c1[r] = P.dx * A(r, 1), c2[r] = P.dx * A(r, 2);
-            }
-            cell = base[0] | (base[1] << 10) | (base[2] << 20);
-            float4* my = &pkt[warp][lane * CH];
-#pragma unroll
-            for (int jj = 0; jj < 3; ++jj) {
-                float tj[D];
-#pragma unroll
-                for (int r = 0; r < D; ++r) tj[r] = (jj == 0) ? b[r] : (jj == 1) ? b[r] + c1[r] : fmaf(c1[r], 2.0f, b[r]);
-#pragma unroll
-                for (int kk = 0; kk < 3; ++kk) {
-                    float q[D];
-#pragma unroll
-                    for (int r = 0; r < D; ++r) q[r] = (kk == 0) ? tj[r] : (kk == 1) ? tj[r] + c2[r] : fmaf(c2[r], 2.0f, tj[r]);
-                    my[jj * 3 + kk] = make_float4(q[0], q[1], q[2], w[1][jj] * w[2][kk]);
-                }
-            }
-            my[9] = make_float4(c0[0], c0[1], c0[2], p.mass);
-            my[10] = make_float4(w[0][0], w[0][1], w[0][2], __int_as_float(cell));
-        }
-        {   // anchor = tile of the majority of this chunk's particles (warp-uniform)
-            const int tile = (cell >= 0) ? (cell & ~kTileMask3) : (-1 - lane);  // invalid lanes match nobody
-            const unsigned peers = __match_any_sync(0xffffffffu, tile);
-            const int score = (cell >= 0) ? ((__popc(peers) << 5) | (31 - lane)) : 0;
-            const int best = __reduce_max_sync(0xffffffffu, score);
-            const int maj = __shfl_sync(0xffffffffu, tile, 31 - (best & 31));
-            if (maj != anchor) {
-                if (anchor >= 0) window_flush();
-                anchor = maj;
-            }
-        }
-        __syncwarp();
-
-        // ---- phase B (lane = group g, stencil column (j,k); nodes i = 0,1,2 in registers) -------
-        const int s_begin = 11 * g;
-        const int s_cnt = worker ? (min((g == 2) ? 32 : s_begin + 11, cnt) - s_begin) : 0;
-        const float4* pp = &pkt[warp][(worker ? s_begin : 0) * CH];
-        for (int u = 0; u < 11; ++u, pp += CH) {
-            const bool valid = u < s_cnt;
-            float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f), cc = a, x = a;
-            int next = cur;
-            if (valid) {
-                a = pp[jk], cc = pp[9], x = pp[10];
-                next = __float_as_int(x.w);
-                if (cur < 0) cur = next;
-            }
-            unsigned m = __ballot_sync(0xffffffffu, next != cur);
-            while (m) {  // one pass per group whose run ends here (the window is shared by the three groups)
-                const int gs = (__ffs(m) - 1) / 9;
-                if (worker && g == gs) {
-                    flush_acc(cur);
-                    cur = next;
-                }
-                m &= ~(0x1FFu << (9 * gs));
-                __syncwarp();
-            }
-            if (valid) {
-                const float w0 = x.x * a.w, w1 = x.y * a.w, w2 = x.z * a.w;
-                const float2 q0 = make_float2(a.x, a.y), c01 = make_float2(cc.x, cc.y);
-                const float2 q1 = __fadd2_rn(q0, c01), q2 = ffma2(c01, splat2(2.0f), q0);
-                const float z1 = a.z + cc.z, z2 = fmaf(cc.z, 2.0f, a.z);
-                acc01[0] = ffma2(splat2(w0), q0, acc01[0]), acc2[0] = fmaf(w0, a.z, acc2[0]), accm[0] = fmaf(w0, cc.w, accm[0]);
-                acc01[1] = ffma2(splat2(w1), q1, acc01[1]), acc2[1] = fmaf(w1, z1, acc2[1]), accm[1] = fmaf(w1, cc.w, accm[1]);
-                acc01[2] = ffma2(splat2(w2), q2, acc01[2]), acc2[2] = fmaf(w2, z2, acc2[2]), accm[2] = fmaf(w2, cc.w, accm[2]);
-            }
-        }
-        __syncwarp();  // the packets are overwritten by the next chunk
-    }
-#pragma unroll 1
-    for (int gs = 0; gs < 3; ++gs) {
-        if (worker && g == gs && cur >= 0) flush_acc(cur);
-        __syncwarp();
-    }
-    if (anchor >= 0) window_flush();
-}
-
-inline int p2g_window_chunks(uint32_t n) {
-    const uint32_t c = n / (8u * 148u * 6u * kP2GWarps * 32u);  // >= 8 resident waves of CTAs
-    return (int) (c < 1u ? 1u : (c > 16u ? 16u : c));
-}
-
-template <int D, int MODEL, int MINB>
-inline void launch_p2g_cell8(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
-                             float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st, int chunks = 0) {
-    if constexpr (D == 3) {
-        if (chunks <= 0) chunks = p2g_window_chunks(n);
-        const unsigned per_block = kP2GWarps * 32 * chunks;
-        const unsigned blocks = (n + per_block - 1) / per_block;
-        k_p2g_cell8<MODEL, MINB><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys, chunks);
-    } else {
-        const unsigned blocks = (n + kP2GWarps * 32 - 1) / (kP2GWarps * 32);
-        k_p2g_cell<D, MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
-    }
-}
-
 // particles per warp = 32 * chunks; fewer chunks on small scenes so that the grid still fills the GPU
 inline int p2g_stream_chunks(uint32_t n) {
     const uint32_t per_wave = 148u * 6u * kP2GWarps * 32u;  // slots of one resident wave at chunks = 1
