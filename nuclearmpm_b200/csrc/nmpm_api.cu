@@ -545,6 +545,8 @@ static int do_p2g(nmpm_sim* h) {
     } else if (variant >= 70 && variant < 80) {  // experiments: 7C = C chunks per warp
         NMPM_DISPATCH(h, (launch_p2g_cell7<D, MODEL, 6>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream,
                                                         variant - 70)));
+    } else if (variant == 9) {
+        NMPM_DISPATCH(h, (launch_p2g_cell5<D, MODEL, 6, true>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
     } else if (variant == 5) {
         NMPM_DISPATCH(h, (launch_p2g_cell5<D, MODEL, 8>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
     } else if (variant == 6) {

@@ -370,14 +370,23 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell3(ParticleStor
 // of 38 per pair step), and the per-lane math drops to 16 instructions per particle for its 3 nodes.
 // Groups walk contiguous thirds of the warp's slots ([0,11) [11,22) [22,32)) one particle at a time: no
 // pair packing, hence no "segment ends inside a pair" path.
-template <int MODEL, int MINB>
+//
+// BULK = true: a finished run leaves the SM through the TMA instead of the LSU.  A vector reduction costs the
+// LSU ~1.3 cycles per lane (27 lanes = 35 cycles per run, more than half of the kernel's L1 data-pipe load
+// between two re-binnings, profiles/r01h), so the group stages its 27 nodes in shared memory (three 128-bit
+// stores per lane) and each of its 9 lanes hands ONE 48-byte row (the three z-adjacent nodes of an (i,j)
+// pair are contiguous in the grid) to `cp.reduce.async.bulk ... .add.f32`.  Staging slots are a ring of 2
+// per group, recycled after `cp.async.bulk.wait_group.read`.
+template <int MODEL, int MINB, bool BULK>
 __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell5(ParticleStore S, const uint32_t* __restrict__ perm,
                                                                    uint32_t n, MaterialParams P, float4* __restrict__ grid,
                                                                    int* __restrict__ error_flag,
                                                                    const uint32_t* __restrict__ gone_keys) {
     constexpr int D = 3;
     constexpr int CH = 11;  // float4 chunks per particle; odd stride: conflict-free 128-bit stores (lane = slot)
+    constexpr int RING = 2, STG = 28;  // staging: 27 nodes (+1 pad) of 16 B per slot
     __shared__ float4 pkt[kP2GWarps][32 * CH];
+    __shared__ __align__(128) float4 stage[BULK ? kP2GWarps * 3 * RING * STG : 1];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t first = (blockIdx.x * kP2GWarps + warp) * 32u;
@@ -442,12 +451,35 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell5(ParticleStor
 #pragma unroll
     for (int i = 0; i < 3; ++i) acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
 
+    int nflush = 0;
     auto flush = [&](int node) {
-        float4* dst = gcol + node;
+        if constexpr (BULK) {
+            const unsigned gmask = 0x1FFu << (9 * g);  // the 9 lanes of this group are converged here
+            float4* slot = stage + ((warp * 3 + g) * RING + (nflush & (RING - 1))) * STG;
+            if (nflush >= RING) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(RING - 1) : "memory");
+            __syncwarp(gmask);  // every lane's row of the previous use of this slot has been read
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            red_add_f32x4(dst + i * plane, make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]));
-            acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
+            for (int i = 0; i < 3; ++i) {
+                slot[i * 9 + jk] = make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]);
+                acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores -> visible to the async proxy
+            __syncwarp(gmask);
+            // lane jk owns row (i', j') = (jk / 3, jk % 3): nodes (i', j', 0..2), 48 contiguous bytes
+            const float4* src = slot + jk * 3;
+            float4* dst = grid + (node + j * plane + k * n1);  // (i', j') == (j, k) of this lane's jk
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
+                         "r"((uint32_t) __cvta_generic_to_shared(src)), "r"(48)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            ++nflush;
+        } else {
+            float4* dst = gcol + node;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                red_add_f32x4(dst + i * plane, make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]));
+                acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
+            }
         }
     };
 
@@ -469,6 +501,7 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell5(ParticleStor
         acc01[2] = ffma2(splat2(w2), q2, acc01[2]), acc2[2] = fmaf(w2, z2, acc2[2]), accm[2] = fmaf(w2, c.w, accm[2]);
     }
     flush(cur);
+    if constexpr (BULK) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory outlives the reads
 }
 
 // ---- K2 (variant 7, 3D): variant 5 with three particle STREAMS per warp -------------------------
@@ -613,12 +646,12 @@ inline void launch_p2g_cell7(const ParticleStore& S, const uint32_t* perm, uint3
     }
 }
 
-template <int D, int MODEL, int MINB>
+template <int D, int MODEL, int MINB, bool BULK = false>
 inline void launch_p2g_cell5(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
                              float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st) {
     const unsigned blocks = (n + kP2GWarps * 32 - 1) / (kP2GWarps * 32);
     if constexpr (D == 3) {
-        k_p2g_cell5<MODEL, MINB><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
+        k_p2g_cell5<MODEL, MINB, BULK><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
     } else {
         k_p2g_cell<D, MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
     }

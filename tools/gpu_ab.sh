@@ -5,7 +5,7 @@
 tag=${1:-ab}; combos=${2:-"0:4"}; nv=${3:-0}; nb=${4:-}; skip=${5:-28}; wl=${6:-"cfg4 snow128"}
 out=gpurun_out/$tag
 mkdir -p $out
-python -m pytest tests -m gpu -x -q > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 $out/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 $out/pytest_gpu.log
 summ() {
   python - "$1" "$2" <<'PY'
 import json,sys
