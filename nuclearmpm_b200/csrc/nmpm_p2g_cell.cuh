@@ -20,6 +20,8 @@
 // reductions (ppc = particles per cell; 3.4 at 8 ppc in 3D), and no shared-memory float atomics are
 // used at all — on sm_100a those are CAS loops (ATOMS.CAST.SPIN), see DESIGN.md.
 #pragma once
+#include <cuda.h>  // CUtensorMap (the grid as a 4-D float tensor, for the TMA reduce of variant 10)
+
 #include "nmpm_kernels.cuh"
 
 namespace nmpm {
@@ -377,14 +379,18 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell3(ParticleStor
 // stores per lane) and each of its 9 lanes hands ONE 48-byte row (the three z-adjacent nodes of an (i,j)
 // pair are contiguous in the grid) to `cp.reduce.async.bulk ... .add.f32`.  Staging slots are a ring of 2
 // per group, recycled after `cp.async.bulk.wait_group.read`.
-template <int MODEL, int MINB, bool BULK>
+// BULK = 2: the same with ONE `cp.reduce.async.bulk.tensor.4d` per run: the grid is described to the TMA as a
+// float tensor (4, n1, n1, n1) and the staged 3x3x3-node box is added at (0, z, y, x) of the run's base node
+// (UBLKRED / UTMAREDG take warp-uniform operands, so BULK = 1 serialises its nine row copies).
+template <int MODEL, int MINB, int BULK>
 __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell5(ParticleStore S, const uint32_t* __restrict__ perm,
                                                                    uint32_t n, MaterialParams P, float4* __restrict__ grid,
                                                                    int* __restrict__ error_flag,
-                                                                   const uint32_t* __restrict__ gone_keys) {
+                                                                   const uint32_t* __restrict__ gone_keys,
+                                                                   const __grid_constant__ CUtensorMap tmap) {
     constexpr int D = 3;
     constexpr int CH = 11;  // float4 chunks per particle; odd stride: conflict-free 128-bit stores (lane = slot)
-    constexpr int RING = 2, STG = 28;  // staging: 27 nodes (+1 pad) of 16 B per slot
+    constexpr int RING = 2, STG = 32;  // staging: 27 nodes of 16 B per slot, slots 128-byte aligned (TMA tensor source)
     __shared__ float4 pkt[kP2GWarps][32 * CH];
     __shared__ __align__(128) float4 stage[BULK ? kP2GWarps * 3 * RING * STG : 1];
 
@@ -433,7 +439,9 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell5(ParticleStor
             }
         }
         my[9] = make_float4(c0[0], c0[1], c0[2], p.mass);
-        my[10] = make_float4(w[0][0], w[0][1], w[0][2], __int_as_float((base[0] * n1 + base[1]) * n1 + base[2]));
+        // run id: linear base node, or (BULK = 2) the packed base cell x | y << 10 | z << 20 = the TMA coordinates
+        const int code = (BULK == 2) ? (base[0] | (base[1] << 10) | (base[2] << 20)) : ((base[0] * n1 + base[1]) * n1 + base[2]);
+        my[10] = make_float4(w[0][0], w[0][1], w[0][2], __int_as_float(code));
     }
     __syncwarp();
 
@@ -453,7 +461,28 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell5(ParticleStor
 
     int nflush = 0;
     auto flush = [&](int node) {
-        if constexpr (BULK) {
+        if constexpr (BULK == 2) {
+            const unsigned gmask = 0x1FFu << (9 * g);  // the 9 lanes of this group are converged here
+            float4* slot = stage + ((warp * 3 + g) * RING + (nflush & (RING - 1))) * STG;
+            if (jk == 0 && nflush >= RING) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(RING - 1) : "memory");
+            __syncwarp(gmask);  // the previous use of this slot has been read by the TMA
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                slot[i * 9 + jk] = make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]);
+                acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy
+            __syncwarp(gmask);
+            if (jk == 0) {
+                asm volatile(
+                    "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmap),
+                    "r"(0), "r"(node >> 20), "r"((node >> 10) & 1023), "r"(node & 1023),
+                    "r"((uint32_t) __cvta_generic_to_shared(slot))
+                    : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            ++nflush;
+        } else if constexpr (BULK == 1) {
             const unsigned gmask = 0x1FFu << (9 * g);  // the 9 lanes of this group are converged here
             float4* slot = stage + ((warp * 3 + g) * RING + (nflush & (RING - 1))) * STG;
             if (nflush >= RING) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(RING - 1) : "memory");
@@ -463,7 +492,7 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell5(ParticleStor
                 slot[i * 9 + jk] = make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]);
                 acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
             }
-            asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores -> visible to the async proxy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy
             __syncwarp(gmask);
             // lane jk owns row (i', j') = (jk / 3, jk % 3): nodes (i', j', 0..2), 48 contiguous bytes
             const float4* src = slot + jk * 3;
@@ -501,7 +530,7 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell5(ParticleStor
         acc01[2] = ffma2(splat2(w2), q2, acc01[2]), acc2[2] = fmaf(w2, z2, acc2[2]), accm[2] = fmaf(w2, c.w, accm[2]);
     }
     flush(cur);
-    if constexpr (BULK) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory outlives the reads
+    if constexpr (BULK != 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory outlives the reads
 }
 
 // ---- K2 (variant 7, 3D): variant 5 with three particle STREAMS per warp -------------------------
@@ -646,12 +675,15 @@ inline void launch_p2g_cell7(const ParticleStore& S, const uint32_t* perm, uint3
     }
 }
 
-template <int D, int MODEL, int MINB, bool BULK = false>
+template <int D, int MODEL, int MINB, int BULK = 0>
 inline void launch_p2g_cell5(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
-                             float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st) {
+                             float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st,
+                             const CUtensorMap* tmap = nullptr) {
     const unsigned blocks = (n + kP2GWarps * 32 - 1) / (kP2GWarps * 32);
     if constexpr (D == 3) {
-        k_p2g_cell5<MODEL, MINB, BULK><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
+        static const CUtensorMap no_map{};
+        k_p2g_cell5<MODEL, MINB, BULK><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys,
+                                                                          tmap ? *tmap : no_map);
     } else {
         k_p2g_cell<D, MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
     }

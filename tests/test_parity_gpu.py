@@ -119,7 +119,7 @@ def test_radix_sort_large_random_keys():
 
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("model", MODELS)
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 72, 74, 9])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 72, 74, 9, 10])
 def test_one_step_from_random_state(golden, dim, model, variant):
     """Whole step from a random (v,F,C,Jp,mass,volume) state, phase by phase: stress, post-P2G grid
     (+ conservation), post-grid_op grid, particle state."""
@@ -218,7 +218,7 @@ def test_variants_and_sort_cadence_agree(dim):
     n = 5000
     x = rng.uniform(0.35, 0.65, (n, dim)).astype(np.float32)
     ref = None
-    for variant, sort_every in [(1, 0), (1, 1), (2, 1), (2, 3), (3, 1), (3, 3), (4, 4), (5, 1), (5, 3), (6, 4), (7, 1), (7, 4), (73, 3), (9, 1), (9, 4)]:
+    for variant, sort_every in [(1, 0), (1, 1), (2, 1), (2, 3), (3, 1), (3, 3), (4, 4), (5, 1), (5, 3), (6, 4), (7, 1), (7, 4), (73, 3), (9, 1), (9, 4), (10, 1), (10, 4)]:
         sim = nm.MPMSimulation(x, co.JELLY, 64, p2g_variant=variant, sort_every=sort_every)
         sim.advance(20)
         st = sim.particles()
@@ -238,13 +238,13 @@ def test_p2g_group_kernel_ragged_counts(model):
         x = rng.uniform(0.40, 0.48, (n, 3)).astype(np.float32)   # a few cells: long and short segments
         v = rng.normal(size=(n, 3)).astype(np.float32)
         grids = {}
-        for variant in (1, 3, 4, 5, 6, 7, 72, 74, 9):
+        for variant in (1, 3, 4, 5, 6, 7, 72, 74, 9, 10):
             sim = nm.MPMSimulation(x, model, 32, v=v, p2g_variant=variant, sort_every=1)
             sim.phase(0)
             grids[variant] = sim.grid()
         gv1, gm1 = grids[1]
         assert np.isclose(gm1.astype(np.float64).sum(), n, rtol=1e-6)
-        for variant in (3, 4, 5, 6, 7, 72, 74, 9):
+        for variant in (3, 4, 5, 6, 7, 72, 74, 9, 10):
             gv, gm = grids[variant]
             check_grid(gv, gm, gv1, gm1, f"n={n} variant {variant}")
             assert np.isclose(gm.astype(np.float64).sum(), n, rtol=1e-6)
