@@ -49,11 +49,11 @@ typedef struct nmpm_options {
     int device;       /* CUDA device ordinal (default 0) */
     int sort_every;   /* re-bin + radix-sort particles by cell key every k steps (default 4; 0 = never).
                          Between sorts particles keep their last cell order; only float summation order changes */
-    int p2g_variant;  /* 0 = auto, 1 = per-particle float4 REDs, 2 = cell-segmented, lane = node, 3/4 = cell-segmented, 3 groups x (j,k) lanes, particle pairs (3D; 2D runs 2; 80/64 regs),
-                         5/6 = same lanes, per-column packets, one particle per group step (64/80 regs),
-                         7 = 5 with three particle streams per warp over 32*C slots (7C: C chunks forced),
-                         9 = 6 with finished runs leaving through cp.reduce.async.bulk (TMA, nine 48-byte rows) instead of vector REDs,
-                         10 = 9 with one cp.reduce.async.bulk.tensor.4d per run (the grid as a TMA tensor) */
+    int p2g_variant;  /* 0 = auto (3D with binning: 3, or 4 from 8 Mi particles; 2D with binning: 2; no binning: 1),
+                         1 = per-particle float4 REDs,
+                         2 = cell-segmented, lane = stencil node,
+                         3 = cell-segmented, three 9-lane groups per warp, lane = stencil column (3D; 2D runs 2),
+                         4 = 3 on three particle streams per warp over 32*C slots (4C, C = 1..9: C forced) */
     int use_graph;    /* capture the step into a CUDA graph and replay it (default 1) */
     int slab_x0;      /* multi-GPU x-slab: this sim owns particles with slab_x0 <= base.x < slab_x1 */
     int slab_x1;      /* 0 (default) = not a slab: the sim owns the whole domain */

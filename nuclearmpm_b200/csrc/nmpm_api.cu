@@ -10,7 +10,6 @@
 #include <vector>
 
 #include <cuda_runtime.h>
-#include <cudaTypedefs.h>  // PFN_cuTensorMapEncodeTiled
 
 #include "../../include/nmpm.h"
 #include "nmpm_kernels.cuh"
@@ -52,8 +51,6 @@ struct nmpm_sim {
     ParticleStore store[2]{};
     int cur = 0;
     float4* grid = nullptr;
-    CUtensorMap grid_tmap{};  // 3D: the grid as a float tensor (4, n1, n1, n1) with a (4,3,3,3) box, for the TMA reduce
-    bool grid_tmap_ok = false;
     // node boxes (GridBox, device): box[box_cur] bounds the particles of the current step, box[(box_cur+2)%3]
     // the nodes the previous P2G wrote (cleared at the start of the next one), box[(box_cur+1)%3] is being
     // built by the G2P in flight
@@ -271,23 +268,6 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
     if (int rc = alloc_store(h, h->store[1])) return rc;
     CUDA_TRY(h, cudaMalloc(&h->grid, h->cells * sizeof(float4)));
     CUDA_TRY(h, cudaMemset(h->grid, 0, h->cells * sizeof(float4)));  // the only dense clear; afterwards box by box
-    if (h->dim == 3) {  // tensor map of the grid for P2G variant 10 (driver entry point taken through the runtime: no -lcuda)
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
-            qres == cudaDriverEntryPointSuccess) {
-            const cuuint64_t n1 = (cuuint64_t) h->res + 1;
-            const cuuint64_t gdim[4] = {4, n1, n1, n1};
-            const cuuint64_t gstr[3] = {16, 16 * n1, 16 * n1 * n1};  // bytes, dimensions 1..3
-            const cuuint32_t box[4] = {4, 3, 3, 3}, estr[4] = {1, 1, 1, 1};
-            const CUresult r = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn)(
-                &h->grid_tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, h->grid, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            h->grid_tmap_ok = (r == CUDA_SUCCESS);
-        } else {
-            (void) cudaGetLastError();
-        }
-    }
     CUDA_TRY(h, cudaMalloc(&h->d_box, 3 * sizeof(GridBox)));
     CUDA_TRY(h, cudaMalloc(&h->d_box_partial, ((h->cap + 127) / 128 * 4 + 4) * 8 * sizeof(int)));
     for (int k = 0; k < 3; ++k) k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + k);
@@ -557,29 +537,14 @@ static int do_p2g(nmpm_sim* h) {
     int variant = h->opt.p2g_variant;
     // auto: per-particle reductions without binning; with binning the per-column-packet kernel, on three streams per
     // warp once the scene is large enough for the reductions to miss L2 (measured: profiles/r01g)
-    if (variant == 0) variant = (h->opt.sort_every > 0) ? ((h->dim == 3 && h->n >= ((size_t) 8 << 20)) ? 7 : 6) : 1;
-    if (variant == 3) {
-        NMPM_DISPATCH(h, (launch_p2g_cell3<D, MODEL, 6>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
-    } else if (variant == 7) {
-        NMPM_DISPATCH(h, (launch_p2g_cell7<D, MODEL, 6>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
-    } else if (variant >= 70 && variant < 80) {  // experiments: 7C = C chunks per warp
-        NMPM_DISPATCH(h, (launch_p2g_cell7<D, MODEL, 6>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream,
-                                                        variant - 70)));
-    } else if (variant == 10) {
-        if (h->dim == 3 && !h->grid_tmap_ok) {
-            h->last_error = "p2g_variant 10 needs cuTensorMapEncodeTiled (driver too old?)";
-            return NMPM_ERR_INVALID;
-        }
-        NMPM_DISPATCH(h, (launch_p2g_cell5<D, MODEL, 6, 2>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream,
-                                                           &h->grid_tmap)));
-    } else if (variant == 9) {
-        NMPM_DISPATCH(h, (launch_p2g_cell5<D, MODEL, 6, 1>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
-    } else if (variant == 5) {
-        NMPM_DISPATCH(h, (launch_p2g_cell5<D, MODEL, 8>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
-    } else if (variant == 6) {
-        NMPM_DISPATCH(h, (launch_p2g_cell5<D, MODEL, 6>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
-    } else if (variant == 4) {
-        NMPM_DISPATCH(h, (launch_p2g_cell3<D, MODEL, 8>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
+    if (variant == 0) variant = (h->opt.sort_every > 0) ? ((h->dim == 3 && h->n >= ((size_t) 8 << 20)) ? 4 : 3) : 1;
+    if (variant == 4) {
+        NMPM_DISPATCH(h, (launch_p2g_streams<D, MODEL>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
+    } else if (variant > 40 && variant < 50) {  // tests / experiments: 4C = C chunks of 32 slots per warp
+        NMPM_DISPATCH(h, (launch_p2g_streams<D, MODEL>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream,
+                                                       variant - 40)));
+    } else if (variant == 3) {
+        NMPM_DISPATCH(h, (launch_p2g_cols<D, MODEL>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
     } else if (variant == 2) {
         NMPM_DISPATCH(h, (launch_p2g_cell<D, MODEL>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
     } else {

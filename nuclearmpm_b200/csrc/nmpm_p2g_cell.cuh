@@ -20,13 +20,12 @@
 // reductions (ppc = particles per cell; 3.4 at 8 ppc in 3D), and no shared-memory float atomics are
 // used at all — on sm_100a those are CAS loops (ATOMS.CAST.SPIN), see DESIGN.md.
 #pragma once
-#include <cuda.h>  // CUtensorMap (the grid as a 4-D float tensor, for the TMA reduce of variant 10)
-
 #include "nmpm_kernels.cuh"
 
 namespace nmpm {
 
 constexpr int kP2GWarps = 4;
+constexpr int kP2GColsMinB = 6;  // CTAs per SM of the column-lane kernels: 80 registers, no spills in the node walk
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
@@ -192,207 +191,31 @@ __global__ void __launch_bounds__(kP2GWarps * 32, NMPM_P2G_MINB) k_p2g_cell(Part
     flush(cur);
 }
 
-// ---- K2 (variant 3, 3D): three particle pairs per warp step, three nodes per lane ---------------
+// ---- K2 (variant 3, 3D): three 9-lane groups per warp, lane = stencil column, per-column packets --
 //
-// Same phase A as above.  Phase B changes the lane <-> work mapping: the 27 active lanes form THREE
-// groups of 9; group g walks its own contiguous third of the warp's 32 cell-sorted slots (pairs
-// [0,6), [6,11), [11,16)), a lane is the (j,k) column of the stencil and owns its three nodes
-// i = 0,1,2 in registers.  Per pair of particles a lane then needs
-//     wyz = wy[j] wz[k];  base_r = b_r + A'_r1 j + A'_r2 k;  val_i = base + i A'_.0;  w_i = wx[i] wyz
-//     acc_i += w_i (val_i, m)                                     -> 28 packed fp32x2 instructions
-// for 3 nodes x 2 particles (4.7 per node-particle instead of 7.5), and the warp retires 6 particles per
-// step of 11 shared-memory loads instead of 2: 66 LDS per 32 particles instead of 176 (the v2 loop was
-// MIO-throttled, profiles/r01d_ncu_summary.md).  A segment (run of particles of one cell) that ends
-// costs three vector reductions per lane, as before one per node.
-template <int MODEL, int MINB>
-__global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell3(ParticleStore S, const uint32_t* __restrict__ perm,
-                                                                            uint32_t n, MaterialParams P, float4* __restrict__ grid,
-                                                                            int* __restrict__ error_flag,
-                                                                            const uint32_t* __restrict__ gone_keys) {
-    constexpr int D = 3;
-    constexpr int NV = 16;   // b(3) m | A' col1(3) col2(3) col0(3) | wx(3)
-    constexpr int NQ4 = 8;   // float4 words per particle PAIR
-    constexpr int WSTRIDE = 34;
-    // pk[warp][q][t] = { val_{2q}(2t), val_{2q}(2t+1), val_{2q+1}(2t), val_{2q+1}(2t+1) }
-    __shared__ float4 pk[kP2GWarps][NQ4][16];
-    __shared__ __align__(8) float wt[kP2GWarps][6][WSTRIDE];  // rows 0..2: wy[j], 3..5: wz[k]; column = slot
-    __shared__ __align__(8) int node0[kP2GWarps][32];
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t first = (blockIdx.x * kP2GWarps + warp) * 32u;
-    if (first >= n) return;
-    const int cnt = min(32u, n - first);
-    const int n1 = P.n1;
-
-    // ---- phase A (lane = particle) ----------------------------------------------------------
-    {
-        float vals[NV];
-        float w[D][3];
-        int nd = -1;
-#pragma unroll
-        for (int k = 0; k < NV; ++k) vals[k] = 0.0f;
-#pragma unroll
-        for (int d = 0; d < D; ++d) w[d][0] = w[d][1] = w[d][2] = 0.0f;
-        if (lane < cnt) {
-            PState<D> p;
-            load_for_p2g<D>(S, perm ? __ldg(perm + first + lane) : first + lane, p);
-            int base[D];
-            float fx[D];
-            if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
-            const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, p.mass, p.volume, P);
-            const bool gone = gone_keys && __ldg(gone_keys + first + lane) == kKeyGone;
-            if (gone) {
-                p.mass = 0.0f;
-#pragma unroll
-                for (int d = 0; d < D; ++d) w[d][0] = w[d][1] = w[d][2] = 0.0f;
-            }
-#pragma unroll
-            for (int r = 0; r < D; ++r) {
-                float afx = A(r, 0) * fx[0];
-#pragma unroll
-                for (int k = 1; k < D; ++k) afx = fmaf(A(r, k), fx[k], afx);
-                vals[r] = gone ? 0.0f : fmaf(-P.dx, afx, p.v[r] * p.mass);  // b_r
-                vals[4 + r] = gone ? 0.0f : P.dx * A(r, 1);
-                vals[7 + r] = gone ? 0.0f : P.dx * A(r, 2);
-                vals[10 + r] = gone ? 0.0f : P.dx * A(r, 0);
-            }
-            vals[3] = p.mass;
-            vals[13] = w[0][0], vals[14] = w[0][1], vals[15] = w[0][2];
-            nd = (base[0] * n1 + base[1]) * n1 + base[2];
-        }
-        float* pkf = reinterpret_cast<float*>(&pk[warp][0][0]);
-        const int t = lane >> 1, h = lane & 1;
-#pragma unroll
-        for (int k = 0; k < NV; ++k) pkf[((k >> 1) * 16 + t) * 4 + (k & 1) * 2 + h] = vals[k];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            wt[warp][i][lane] = w[1][i];
-            wt[warp][3 + i][lane] = w[2][i];
-        }
-        node0[warp][lane] = nd;
-    }
-    __syncwarp();
-
-    // ---- phase B (lane = group g, stencil column (j,k); nodes i = 0,1,2 in registers) ---------
-    if (lane >= 27) return;
-    const int g = lane / 9, jk = lane - 9 * g, j = jk / 3, k = jk - 3 * j;
-    const int t_begin = (g == 0) ? 0 : (g == 1) ? 6 : 11;
-    const int t_end = min((g == 0) ? 6 : (g == 1) ? 11 : 16, (cnt + 1) >> 1);
-    if (t_begin >= t_end) return;
-    const float2 jf = splat2((float) j), kf = splat2((float) k), two = splat2(2.0f);
-    const float* wy = &wt[warp][j][0];
-    const float* wz = &wt[warp][3 + k][0];
-    const int off0 = j * n1 + k, plane = n1 * n1;
-
-    float2 acc[3][D], acc_m[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        acc_m[i] = splat2(0.0f);
-#pragma unroll
-        for (int r = 0; r < D; ++r) acc[i][r] = splat2(0.0f);
-    }
-    int cur = node0[warp][2 * t_begin];
-
-    auto flush = [&](int node) {
-        float4* dst = grid + (size_t) (node + off0);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            red_add_f32x4(dst + (size_t) i * plane,
-                          make_float4(acc[i][0].x + acc[i][0].y, acc[i][1].x + acc[i][1].y, acc[i][2].x + acc[i][2].y,
-                                      acc_m[i].x + acc_m[i].y));
-            acc_m[i] = splat2(0.0f);
-#pragma unroll
-            for (int r = 0; r < D; ++r) acc[i][r] = splat2(0.0f);
-        }
-    };
-
-    for (int t = t_begin; t < t_end; ++t) {
-        int2 nn = *reinterpret_cast<const int2*>(&node0[warp][2 * t]);
-        float2 val[NV];
-#pragma unroll
-        for (int q = 0; q < NQ4; ++q) {
-            const float4 f = pk[warp][q][t];
-            val[2 * q] = make_float2(f.x, f.y);
-            val[2 * q + 1] = make_float2(f.z, f.w);
-        }
-        const float2 wyz = fmul2(*reinterpret_cast<const float2*>(wy + 2 * t), *reinterpret_cast<const float2*>(wz + 2 * t));
-        float2 q[3][D], w[3];
-#pragma unroll
-        for (int r = 0; r < D; ++r) {
-            q[0][r] = ffma2(val[7 + r], kf, ffma2(val[4 + r], jf, val[r]));
-            q[1][r] = __fadd2_rn(q[0][r], val[10 + r]);
-            q[2][r] = ffma2(val[10 + r], two, q[0][r]);
-        }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) w[i] = fmul2(val[13 + i], wyz);
-        const float2 mass = val[3];
-        if (nn.y < 0) nn.y = nn.x;  // odd tail: the padding slot has zero weight
-        if (nn.x != cur) {          // a new cell starts with this pair
-            flush(cur);
-            cur = nn.x;
-        }
-        if (nn.y == cur) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-#pragma unroll
-                for (int r = 0; r < D; ++r) acc[i][r] = ffma2(w[i], q[i][r], acc[i][r]);
-                acc_m[i] = ffma2(w[i], mass, acc_m[i]);
-            }
-        } else {  // the cell changes between the two particles of the pair: scalar halves
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-#pragma unroll
-                for (int r = 0; r < D; ++r) acc[i][r].x = fmaf(w[i].x, q[i][r].x, acc[i][r].x);
-                acc_m[i].x = fmaf(w[i].x, mass.x, acc_m[i].x);
-            }
-            flush(cur);
-            cur = nn.y;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-#pragma unroll
-                for (int r = 0; r < D; ++r) acc[i][r].y = fmaf(w[i].y, q[i][r].y, acc[i][r].y);
-                acc_m[i].y = fmaf(w[i].y, mass.y, acc_m[i].y);
-            }
-        }
-    }
-    flush(cur);
-}
-
-// ---- K2 (variant 5, 3D): one particle per group step, lane-specific packets ---------------------
-//
-// ncu on variant 3 (profiles/r01e): the kernel is bound by the L1/shared DATA PIPE (l1tex data-pipe
-// wavefronts 93 % of peak), not by issue slots: a 128-bit shared load costs 4 wavefronts whether or not
-// it is a broadcast, so what matters is the number of BYTES each lane pulls out of shared memory
-// (variant 2: 68 B per lane per particle x 32 lanes; variant 3: 72 B x 27 lanes / 3 groups).
-// Here phase A leaves, per particle, the quantities already specialised per stencil column (j,k):
+// ncu on the lane = node kernel above (profiles/r01d, r01e): it is bound by the L1/shared DATA PIPE (l1tex
+// data-pipe wavefronts 83-93 % of peak), not by issue slots.  A 128-bit shared load costs 4 wavefronts
+// whether or not it is a broadcast, so what matters is how many BYTES each lane pulls out of shared memory
+// (there: 68 B per lane per particle x 32 lanes), and a vector reduction costs ~1.3 LSU cycles per LANE.
+// Here the 27 active lanes form THREE groups of 9; group g walks its own contiguous third of the warp's 32
+// cell-sorted slots ([0,11) [11,22) [22,32)) one particle at a time, a lane is the (j,k) column of the
+// stencil and owns its three nodes i = 0,1,2 in registers.  Phase A leaves, per particle, the quantities
+// already specialised per column:
 //     chunk jk (9x):  { b + A'_.1 j + A'_.2 k  (xyz),  wy[j] wz[k] }        read by ONE lane
 //     chunk 9:        { A'_.0 (xyz), mass }                                  read by the 9 lanes of a group
 //     chunk 10:       { wx[0], wx[1], wx[2], base node }                     read by the 9 lanes of a group
-// so a lane reads 48 B per particle of its group (three LDS.128 = 12 wavefronts per group step instead
-// of 38 per pair step), and the per-lane math drops to 16 instructions per particle for its 3 nodes.
-// Groups walk contiguous thirds of the warp's slots ([0,11) [11,22) [22,32)) one particle at a time: no
-// pair packing, hence no "segment ends inside a pair" path.
-//
-// BULK = true: a finished run leaves the SM through the TMA instead of the LSU.  A vector reduction costs the
-// LSU ~1.3 cycles per lane (27 lanes = 35 cycles per run, more than half of the kernel's L1 data-pipe load
-// between two re-binnings, profiles/r01h), so the group stages its 27 nodes in shared memory (three 128-bit
-// stores per lane) and each of its 9 lanes hands ONE 48-byte row (the three z-adjacent nodes of an (i,j)
-// pair are contiguous in the grid) to `cp.reduce.async.bulk ... .add.f32`.  Staging slots are a ring of 2
-// per group, recycled after `cp.async.bulk.wait_group.read`.
-// BULK = 2: the same with ONE `cp.reduce.async.bulk.tensor.4d` per run: the grid is described to the TMA as a
-// float tensor (4, n1, n1, n1) and the staged 3x3x3-node box is added at (0, z, y, x) of the run's base node
-// (UBLKRED / UTMAREDG take warp-uniform operands, so BULK = 1 serialises its nine row copies).
-template <int MODEL, int MINB, int BULK>
-__global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell5(ParticleStore S, const uint32_t* __restrict__ perm,
-                                                                   uint32_t n, MaterialParams P, float4* __restrict__ grid,
-                                                                   int* __restrict__ error_flag,
-                                                                   const uint32_t* __restrict__ gone_keys,
-                                                                   const __grid_constant__ CUtensorMap tmap) {
+// so a lane reads 48 B per particle of its group (three LDS.128 = 12 wavefronts for 3 particles) and
+// spends 16 math instructions per particle on its 3 nodes: val_i = chunk_jk + i A'_.0, w_i = wx[i] wy wz,
+// acc_i += w_i (val_i, mass).  A run of particles of one cell that ends costs three vector reductions per
+// lane (one per node, as before).
+template <int MODEL>
+__global__ void __launch_bounds__(kP2GWarps * 32, kP2GColsMinB) k_p2g_cols(ParticleStore S, const uint32_t* __restrict__ perm,
+                                                                          uint32_t n, MaterialParams P, float4* __restrict__ grid,
+                                                                          int* __restrict__ error_flag,
+                                                                          const uint32_t* __restrict__ gone_keys) {
     constexpr int D = 3;
     constexpr int CH = 11;  // float4 chunks per particle; odd stride: conflict-free 128-bit stores (lane = slot)
-    constexpr int RING = 2, STG = 32;  // staging: 27 nodes of 16 B per slot, slots 128-byte aligned (TMA tensor source)
     __shared__ float4 pkt[kP2GWarps][32 * CH];
-    __shared__ __align__(128) float4 stage[BULK ? kP2GWarps * 3 * RING * STG : 1];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t first = (blockIdx.x * kP2GWarps + warp) * 32u;
@@ -439,9 +262,7 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell5(ParticleStor
             }
         }
         my[9] = make_float4(c0[0], c0[1], c0[2], p.mass);
-        // run id: linear base node, or (BULK = 2) the packed base cell x | y << 10 | z << 20 = the TMA coordinates
-        const int code = (BULK == 2) ? (base[0] | (base[1] << 10) | (base[2] << 20)) : ((base[0] * n1 + base[1]) * n1 + base[2]);
-        my[10] = make_float4(w[0][0], w[0][1], w[0][2], __int_as_float(code));
+        my[10] = make_float4(w[0][0], w[0][1], w[0][2], __int_as_float((base[0] * n1 + base[1]) * n1 + base[2]));
     }
     __syncwarp();
 
@@ -459,56 +280,12 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell5(ParticleStor
 #pragma unroll
     for (int i = 0; i < 3; ++i) acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
 
-    int nflush = 0;
     auto flush = [&](int node) {
-        if constexpr (BULK == 2) {
-            const unsigned gmask = 0x1FFu << (9 * g);  // the 9 lanes of this group are converged here
-            float4* slot = stage + ((warp * 3 + g) * RING + (nflush & (RING - 1))) * STG;
-            if (jk == 0 && nflush >= RING) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(RING - 1) : "memory");
-            __syncwarp(gmask);  // the previous use of this slot has been read by the TMA
+        float4* dst = gcol + node;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                slot[i * 9 + jk] = make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]);
-                acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy
-            __syncwarp(gmask);
-            if (jk == 0) {
-                asm volatile(
-                    "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmap),
-                    "r"(0), "r"(node >> 20), "r"((node >> 10) & 1023), "r"(node & 1023),
-                    "r"((uint32_t) __cvta_generic_to_shared(slot))
-                    : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-            ++nflush;
-        } else if constexpr (BULK == 1) {
-            const unsigned gmask = 0x1FFu << (9 * g);  // the 9 lanes of this group are converged here
-            float4* slot = stage + ((warp * 3 + g) * RING + (nflush & (RING - 1))) * STG;
-            if (nflush >= RING) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(RING - 1) : "memory");
-            __syncwarp(gmask);  // every lane's row of the previous use of this slot has been read
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                slot[i * 9 + jk] = make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]);
-                acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy
-            __syncwarp(gmask);
-            // lane jk owns row (i', j') = (jk / 3, jk % 3): nodes (i', j', 0..2), 48 contiguous bytes
-            const float4* src = slot + jk * 3;
-            float4* dst = grid + (node + j * plane + k * n1);  // (i', j') == (j, k) of this lane's jk
-            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
-                         "r"((uint32_t) __cvta_generic_to_shared(src)), "r"(48)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            ++nflush;
-        } else {
-            float4* dst = gcol + node;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                red_add_f32x4(dst + i * plane, make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]));
-                acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
-            }
+        for (int i = 0; i < 3; ++i) {
+            red_add_f32x4(dst + i * plane, make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]));
+            acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
         }
     };
 
@@ -530,10 +307,9 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell5(ParticleStor
         acc01[2] = ffma2(splat2(w2), q2, acc01[2]), acc2[2] = fmaf(w2, z2, acc2[2]), accm[2] = fmaf(w2, c.w, accm[2]);
     }
     flush(cur);
-    if constexpr (BULK != 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory outlives the reads
 }
 
-// ---- K2 (variant 7, 3D): variant 5 with three particle STREAMS per warp -------------------------
+// ---- K2 (variant 4, 3D): variant 3 with three particle STREAMS per warp -------------------------
 //
 // A vector reduction costs the SM ~1.3 cycles per LANE (REDG, B300_MICROARCH.md "Atomics"), so the 27
 // lane-reductions of one flushed cell run cost as much as 35 ordinary instructions, and in variants
@@ -542,11 +318,11 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell5(ParticleStor
 // slots.  Per chunk, lanes [0,11) [11,22) [22,32) load the next 11/11/10 particles of streams 0/1/2
 // (phase A), then group g walks them (phase B) with its run accumulators carried from chunk to chunk:
 // the only flushes left are real cell changes plus three per warp, i.e. 3/C per 32 particles.
-template <int MODEL, int MINB>
-__global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_cell7(ParticleStore S, const uint32_t* __restrict__ perm,
-                                                                   uint32_t n, MaterialParams P, float4* __restrict__ grid,
-                                                                   int* __restrict__ error_flag,
-                                                                   const uint32_t* __restrict__ gone_keys, int chunks) {
+template <int MODEL>
+__global__ void __launch_bounds__(kP2GWarps * 32, kP2GColsMinB) k_p2g_streams(ParticleStore S, const uint32_t* __restrict__ perm,
+                                                                             uint32_t n, MaterialParams P,
+                                                                             float4* __restrict__ grid, int* __restrict__ error_flag,
+                                                                             const uint32_t* __restrict__ gone_keys, int chunks) {
     constexpr int D = 3;
     constexpr int CH = 11;  // float4 chunks per particle (see variant 5)
     __shared__ float4 pkt[kP2GWarps][32 * CH];
@@ -661,41 +437,27 @@ inline int p2g_stream_chunks(uint32_t n) {
     return (int) (c < 1u ? 1u : (c > 4u ? 4u : c));
 }
 
-template <int D, int MODEL, int MINB>
-inline void launch_p2g_cell7(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
-                             float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st, int chunks = 0) {
+template <int D, int MODEL>
+inline void launch_p2g_streams(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
+                               float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st, int chunks = 0) {
     if constexpr (D == 3) {
         if (chunks <= 0) chunks = p2g_stream_chunks(n);
         const unsigned per_block = kP2GWarps * 32 * chunks;
         const unsigned blocks = (n + per_block - 1) / per_block;
-        k_p2g_cell7<MODEL, MINB><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys, chunks);
-    } else {
+        k_p2g_streams<MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys, chunks);
+    } else {  // 2D scenes are launch-bound (cfg1: 5 000 particles): the lane = node kernel stays
         const unsigned blocks = (n + kP2GWarps * 32 - 1) / (kP2GWarps * 32);
         k_p2g_cell<D, MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
     }
 }
 
-template <int D, int MODEL, int MINB, int BULK = 0>
-inline void launch_p2g_cell5(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
-                             float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st,
-                             const CUtensorMap* tmap = nullptr) {
+template <int D, int MODEL>
+inline void launch_p2g_cols(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
+                            float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st) {
     const unsigned blocks = (n + kP2GWarps * 32 - 1) / (kP2GWarps * 32);
     if constexpr (D == 3) {
-        static const CUtensorMap no_map{};
-        k_p2g_cell5<MODEL, MINB, BULK><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys,
-                                                                          tmap ? *tmap : no_map);
+        k_p2g_cols<MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
     } else {
-        k_p2g_cell<D, MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
-    }
-}
-
-template <int D, int MODEL, int MINB>
-inline void launch_p2g_cell3(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
-                             float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st) {
-    const unsigned blocks = (n + kP2GWarps * 32 - 1) / (kP2GWarps * 32);
-    if constexpr (D == 3) {
-        k_p2g_cell3<MODEL, MINB><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
-    } else {  // 2D scenes are launch-bound (cfg1: 5 000 particles): the v2 kernel stays
         k_p2g_cell<D, MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
     }
 }

@@ -119,7 +119,7 @@ def test_radix_sort_large_random_keys():
 
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("model", MODELS)
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 72, 74, 9, 10])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 42, 44])
 def test_one_step_from_random_state(golden, dim, model, variant):
     """Whole step from a random (v,F,C,Jp,mass,volume) state, phase by phase: stress, post-P2G grid
     (+ conservation), post-grid_op grid, particle state."""
@@ -218,7 +218,7 @@ def test_variants_and_sort_cadence_agree(dim):
     n = 5000
     x = rng.uniform(0.35, 0.65, (n, dim)).astype(np.float32)
     ref = None
-    for variant, sort_every in [(1, 0), (1, 1), (2, 1), (2, 3), (3, 1), (3, 3), (4, 4), (5, 1), (5, 3), (6, 4), (7, 1), (7, 4), (73, 3), (9, 1), (9, 4), (10, 1), (10, 4)]:
+    for variant, sort_every in [(1, 0), (1, 1), (2, 1), (2, 3), (3, 1), (3, 3), (4, 1), (4, 4), (43, 3)]:
         sim = nm.MPMSimulation(x, co.JELLY, 64, p2g_variant=variant, sort_every=sort_every)
         sim.advance(20)
         st = sim.particles()
@@ -230,21 +230,21 @@ def test_variants_and_sort_cadence_agree(dim):
 
 @pytest.mark.parametrize("model", MODELS)
 def test_p2g_group_kernel_ragged_counts(model):
-    """Variants 3-6 (three 9-lane groups per warp walking thirds of the warp's slots) on particle counts that
-    leave groups empty, end a group on an odd slot, or fill exactly one warp: post-P2G grid against the
-    per-particle scatter (variant 1) on the same cell-sorted state, and mass conservation."""
+    """Variants 3 and 4 (three 9-lane groups per warp walking thirds of the warp's slots / three streams over
+    32*C slots) on particle counts that leave groups or streams empty or short, or fill exactly one warp:
+    post-P2G grid against the per-particle scatter (variant 1) on the same cell-sorted state, mass conservation."""
     rng = np.random.default_rng(17)
     for n in (1, 2, 11, 12, 13, 21, 22, 23, 24, 25, 31, 32, 33, 45, 63, 64, 65, 127, 129, 300, 515):
         x = rng.uniform(0.40, 0.48, (n, 3)).astype(np.float32)   # a few cells: long and short segments
         v = rng.normal(size=(n, 3)).astype(np.float32)
         grids = {}
-        for variant in (1, 3, 4, 5, 6, 7, 72, 74, 9, 10):
+        for variant in (1, 3, 4, 42, 44):
             sim = nm.MPMSimulation(x, model, 32, v=v, p2g_variant=variant, sort_every=1)
             sim.phase(0)
             grids[variant] = sim.grid()
         gv1, gm1 = grids[1]
         assert np.isclose(gm1.astype(np.float64).sum(), n, rtol=1e-6)
-        for variant in (3, 4, 5, 6, 7, 72, 74, 9, 10):
+        for variant in (3, 4, 42, 44):
             gv, gm = grids[variant]
             check_grid(gv, gm, gv1, gm1, f"n={n} variant {variant}")
             assert np.isclose(gm.astype(np.float64).sum(), n, rtol=1e-6)
