@@ -34,6 +34,10 @@ __global__ void __launch_bounds__(256) k_add_planes(float4* __restrict__ dst, co
 }
 }  // namespace
 
+// Ring of node boxes.  Three are needed (previous / current / next); four keeps the ring index in phase with the
+// sort cadence (1, 2, 4, 8), so that the CUDA-graph cache of step_once sees 2*sort_every host states instead of 6x.
+constexpr int kBoxRing = 4;
+
 struct nmpm_sim {
     int dim = 0, model = 0, res = 0;
     size_t n = 0, cells = 0;  // n = live particles (slots [0,n) of store[cur] after a G2P)
@@ -51,8 +55,8 @@ struct nmpm_sim {
     ParticleStore store[2]{};
     int cur = 0;
     float4* grid = nullptr;
-    // node boxes (GridBox, device): box[box_cur] bounds the particles of the current step, box[(box_cur+2)%3]
-    // the nodes the previous P2G wrote (cleared at the start of the next one), box[(box_cur+1)%3] is being
+    // node boxes (GridBox, device): box[box_cur] bounds the particles of the current step, box[(box_cur+3)%4]
+    // the nodes the previous P2G wrote (cleared at the start of the next one), box[(box_cur+1)%4] is being
     // built by the G2P in flight
     GridBox* d_box = nullptr;
     int* d_box_partial = nullptr;  // one partial box (8 ints) per G2P warp
@@ -268,9 +272,9 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
     if (int rc = alloc_store(h, h->store[1])) return rc;
     CUDA_TRY(h, cudaMalloc(&h->grid, h->cells * sizeof(float4)));
     CUDA_TRY(h, cudaMemset(h->grid, 0, h->cells * sizeof(float4)));  // the only dense clear; afterwards box by box
-    CUDA_TRY(h, cudaMalloc(&h->d_box, 3 * sizeof(GridBox)));
+    CUDA_TRY(h, cudaMalloc(&h->d_box, kBoxRing * sizeof(GridBox)));
     CUDA_TRY(h, cudaMalloc(&h->d_box_partial, ((h->cap + 127) / 128 * 4 + 4) * 8 * sizeof(int)));
-    for (int k = 0; k < 3; ++k) k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + k);
+    for (int k = 0; k < kBoxRing; ++k) k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + k);
     CUDA_TRY(h, cudaMalloc(&h->d_error, sizeof(int)));
     CUDA_TRY(h, cudaMemset(h->d_error, 0, sizeof(int)));
     CUDA_TRY(h, cudaMallocHost(&h->h_error, sizeof(int)));
@@ -514,7 +518,7 @@ static int ensure_box(nmpm_sim* h) {
 static int do_p2g(nmpm_sim* h) {
     if (int rc = ensure_box(h)) return rc;
     // K1: clear what the previous P2G (and, for a slab, the neighbours' ghost planes) wrote
-    NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + (h->box_cur + 2) % 3,
+    NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + (h->box_cur + kBoxRing - 1) % kBoxRing,
                                                                             h->P.n1)));
     h->launches++;
     for (const auto& pr : h->dirty_planes)
@@ -540,6 +544,12 @@ static int do_p2g(nmpm_sim* h) {
     if (variant == 0) variant = (h->opt.sort_every > 0) ? ((h->dim == 3 && h->n >= ((size_t) 8 << 20)) ? 4 : 3) : 1;
     if (variant == 4) {
         NMPM_DISPATCH(h, (launch_p2g_streams<D, MODEL>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
+    } else if (variant == 104 || variant == 204) {  // experiments: streams + L1 / L2 prefetch of the next chunk
+        if (variant == 104) {
+            NMPM_DISPATCH(h, (launch_p2g_streams<D, MODEL, 1>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
+        } else {
+            NMPM_DISPATCH(h, (launch_p2g_streams<D, MODEL, 2>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
+        }
     } else if (variant > 40 && variant < 50) {  // tests / experiments: 4C = C chunks of 32 slots per warp
         NMPM_DISPATCH(h, (launch_p2g_streams<D, MODEL>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream,
                                                        variant - 40)));
@@ -564,7 +574,7 @@ static int do_grid_op(nmpm_sim* h) {
 static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullptr, nullptr, 0, nullptr}) {
     if (h->n == 0) {
         h->n_store = 0;
-        h->box_cur = (h->box_cur + 1) % 3;
+        h->box_cur = (h->box_cur + 1) % kBoxRing;
         k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + h->box_cur);
         return NMPM_OK;
     }
@@ -576,7 +586,7 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
     // a slab keeps the key array aligned with the slots at all times: it carries the "migrated away" marks
     uint32_t* keys_out = (next_sorts || h->slab) ? h->sort.keys_a : nullptr;
     const uint32_t* gone_keys = (h->slab && !h->perm && h->n_gone) ? h->sort.keys_a : nullptr;
-    const int box_next = (h->box_cur + 1) % 3;
+    const int box_next = (h->box_cur + 1) % kBoxRing;
     k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + box_next);
     NMPM_DISPATCH(h, (k_g2p_gather<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(
                          S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error, mig,
