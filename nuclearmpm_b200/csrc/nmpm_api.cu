@@ -544,12 +544,6 @@ static int do_p2g(nmpm_sim* h) {
     if (variant == 0) variant = (h->opt.sort_every > 0) ? ((h->dim == 3 && h->n >= ((size_t) 8 << 20)) ? 4 : 3) : 1;
     if (variant == 4) {
         NMPM_DISPATCH(h, (launch_p2g_streams<D, MODEL>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
-    } else if (variant == 104 || variant == 204) {  // experiments: streams + L1 / L2 prefetch of the next chunk
-        if (variant == 104) {
-            NMPM_DISPATCH(h, (launch_p2g_streams<D, MODEL, 1>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
-        } else {
-            NMPM_DISPATCH(h, (launch_p2g_streams<D, MODEL, 2>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
-        }
     } else if (variant > 40 && variant < 50) {  // tests / experiments: 4C = C chunks of 32 slots per warp
         NMPM_DISPATCH(h, (launch_p2g_streams<D, MODEL>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream,
                                                        variant - 40)));

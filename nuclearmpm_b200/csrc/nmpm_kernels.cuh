@@ -432,13 +432,6 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
         // and (plain, z-offset-weighted) sums of the z component, which share their operands.
         const float4* gp = grid + ((size_t) (base[0] * n1 + base[1]) * n1 + base[2]);
         const int plane = n1 * n1;
-#ifdef NMPM_G2P_PREFETCH
-        // experiment: request the nine node rows up front (no registers held), so that the later load batches hit L1
-#pragma unroll
-        for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-            for (int jj = 0; jj < 3; ++jj) asm volatile("prefetch.global.L1 [%0];" ::"l"(gp + (ii * plane + jj * n1)));
-#endif
         const float2 wz0 = splat2g(w[2][0]), wz1 = splat2g(w[2][1]), wz2 = splat2g(w[2][2]), nwz0 = splat2g(-w[2][0]);
         const float2 wzp0 = make_float2(w[2][0], -w[2][0]), wzp1 = make_float2(w[2][1], 0.0f), wzp2 = wz2;
         float2 v01, vzBzz, Bz01, By01, Bx01;  // v.xy | (v.z, B_z.z) | B_z.xy | B_y.xy | B_x.xy

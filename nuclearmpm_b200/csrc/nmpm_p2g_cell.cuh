@@ -318,15 +318,7 @@ __global__ void __launch_bounds__(kP2GWarps * 32, kP2GColsMinB) k_p2g_cols(Parti
 // slots.  Per chunk, lanes [0,11) [11,22) [22,32) load the next 11/11/10 particles of streams 0/1/2
 // (phase A), then group g walks them (phase B) with its run accumulators carried from chunk to chunk:
 // the only flushes left are real cell changes plus three per warp, i.e. 3/C per 32 particles.
-// PF: 0 = no prefetch, 1 / 2 = `prefetch.global.L1 / .L2` of the NEXT chunk's particle rows while this chunk is
-// walked (a warp alternates load -> math -> walk C times with only ~5 warps per scheduler to cover the loads).
-template <int PF>
-__device__ __forceinline__ void prefetch_row(const void* p) {
-    if constexpr (PF == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-    if constexpr (PF == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-template <int MODEL, int PF>
+template <int MODEL>
 __global__ void __launch_bounds__(kP2GWarps * 32, kP2GColsMinB) k_p2g_streams(ParticleStore S, const uint32_t* __restrict__ perm,
                                                                              uint32_t n, MaterialParams P,
                                                                              float4* __restrict__ grid, int* __restrict__ error_flag,
@@ -373,14 +365,6 @@ __global__ void __launch_bounds__(kP2GWarps * 32, kP2GColsMinB) k_p2g_streams(Pa
     for (int c = 0; c < chunks; ++c) {
         // ---- phase A (lane = particle of stream ga) ------------------------------------------
         const int pos = c * wa + ia;
-        if (PF != 0 && pos + wa < len_a) {  // the row this lane loads in the next chunk
-            const uint32_t nslot = first + (uint32_t) (off_a + pos + wa);
-            const size_t nsrc = perm ? __ldg(perm + nslot) : nslot;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) prefetch_row<PF>(S.q[q] + nsrc);
-            prefetch_row<PF>(S.s + nsrc);
-            prefetch_row<PF>(S.mv + nsrc);
-        }
         if (pos < len_a) {
             const uint32_t slot = first + (uint32_t) (off_a + pos);
             PState<D> p;
@@ -453,14 +437,14 @@ inline int p2g_stream_chunks(uint32_t n) {
     return (int) (c < 1u ? 1u : (c > 4u ? 4u : c));
 }
 
-template <int D, int MODEL, int PF = 0>
+template <int D, int MODEL>
 inline void launch_p2g_streams(const ParticleStore& S, const uint32_t* perm, uint32_t n, const MaterialParams& P,
                                float4* grid, int* error_flag, const uint32_t* gone_keys, cudaStream_t st, int chunks = 0) {
     if constexpr (D == 3) {
         if (chunks <= 0) chunks = p2g_stream_chunks(n);
         const unsigned per_block = kP2GWarps * 32 * chunks;
         const unsigned blocks = (n + per_block - 1) / per_block;
-        k_p2g_streams<MODEL, PF><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys, chunks);
+        k_p2g_streams<MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys, chunks);
     } else {  // 2D scenes are launch-bound (cfg1: 5 000 particles): the lane = node kernel stays
         const unsigned blocks = (n + kP2GWarps * 32 - 1) / (kP2GWarps * 32);
         k_p2g_cell<D, MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);
