@@ -65,6 +65,7 @@ struct nmpm_sim {
     std::vector<std::array<int, 5>> dirty_rects;    // slab mode: in-plane rectangles written by the native ghost exchange
     struct nmpm_slab_comm* sc = nullptr;            // native slab step (nmpm_slab_comm.inl)
     bool box_valid = false;   // box[box_cur] describes store[cur]
+    bool p2g_early = false;   // slab mode: the in-place P2G of the coming step was issued before the migrants arrived
     bool grid_valid = false;  // false until the first p2g: the reference's grid() is empty (src/solver.cpp:52-57)
 
     SortWorkspace sort;
@@ -537,7 +538,7 @@ static int do_p2g(nmpm_sim* h) {
     const uint32_t n = (uint32_t) h->n;
     ParticleStore& S = h->store[h->cur];
     // slab mode, step without a sort: slots of migrated-away particles are still in the store
-    const uint32_t* gone_keys = (h->slab && !h->perm && h->n_gone) ? h->sort.keys_a : nullptr;
+    const uint32_t* gone_keys = (h->slab && !h->perm && (h->n_gone || h->p2g_early)) ? h->sort.keys_a : nullptr;
     int variant = h->opt.p2g_variant;
     // auto: per-particle reductions without binning; with binning the per-column-packet kernel, on three streams per
     // warp once the scene is large enough for the reductions to miss L2 (measured: profiles/r01g)
@@ -553,7 +554,7 @@ static int do_p2g(nmpm_sim* h) {
         NMPM_DISPATCH(h, (launch_p2g_cell<D, MODEL>(S, h->perm, n, h->P, h->grid, h->d_error, gone_keys, h->stream)));
     } else {
         NMPM_DISPATCH(h, (k_p2g_scatter<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, h->perm, n, h->P,
-                                                                                            h->grid, h->d_error, gone_keys)));
+                                                                                            h->grid, h->d_error, gone_keys, 0u)));
     }
     h->launches++;
     return NMPM_OK;
@@ -579,7 +580,7 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
     const bool next_sorts = h->opt.sort_every > 0 && ((h->steps_done + 1) % h->opt.sort_every) == 0;
     // a slab keeps the key array aligned with the slots at all times: it carries the "migrated away" marks
     uint32_t* keys_out = (next_sorts || h->slab) ? h->sort.keys_a : nullptr;
-    const uint32_t* gone_keys = (h->slab && !h->perm && h->n_gone) ? h->sort.keys_a : nullptr;
+    const uint32_t* gone_keys = (h->slab && !h->perm && (h->n_gone || h->p2g_early)) ? h->sort.keys_a : nullptr;
     const int box_next = (h->box_cur + 1) % kBoxRing;
     k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + box_next);
     NMPM_DISPATCH(h, (k_g2p_gather<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(
@@ -1071,6 +1072,32 @@ int nmpm_slab_p2g(nmpm_handle h) {
     return NMPM_OK;
 }
 
+}  // extern "C"
+
+// Native slab step only (nmpm_slab_comm.inl): issue the coming step's in-place P2G over the resident slots while the
+// host still waits for the migration table, then scatter the received particles (slots [first_new, n_store)) on top.
+static bool slab_next_step_in_place(const nmpm_sim* h) {
+    return h->slab && !h->timing && h->keys_valid && h->opt.sort_every > 0 && (h->steps_done % h->opt.sort_every) != 0;
+}
+static int slab_p2g_early(nmpm_sim* h) {
+    h->p2g_early = true;  // before nmpm_slab_p2g: its P2G must honour the gone marks although n_gone is not updated yet
+    return nmpm_slab_p2g(h);
+}
+static int slab_p2g_tail(nmpm_sim* h, size_t first_new) {
+    if (h->n_store > first_new) {
+        const uint32_t n = (uint32_t) h->n_store, first = (uint32_t) first_new;
+        NMPM_DISPATCH(h, (k_p2g_scatter<D, MODEL><<<blocks_for(n - first, 128), 128, 0, h->stream>>>(
+                             h->store[h->cur], nullptr, n, h->P, h->grid, h->d_error, nullptr, first)));
+        h->launches++;
+    }
+    h->n = h->n_store;  // grid_op / G2P of this step run over every slot
+    h->p2g_early = false;
+    CUDA_TRY(h, cudaGetLastError());
+    return NMPM_OK;
+}
+
+extern "C" {
+
 int nmpm_slab_grid_g2p(nmpm_handle h, void* send_left, void* send_right, size_t cap_records, int* d_counts) {
     if (int rc = slab_check(h, "nmpm_slab_grid_g2p")) return rc;
     if (!send_left || !send_right || !d_counts || cap_records > 0xFFFFFFF0ull) return NMPM_ERR_INVALID;
@@ -1111,7 +1138,7 @@ int nmpm_slab_unpack(nmpm_handle h, const void* recv_left, size_t n_from_left, c
                      size_t n_from_right, size_t n_sent) {
     if (int rc = slab_check(h, "nmpm_slab_unpack")) return rc;
     if ((n_from_left && !recv_left) || (n_from_right && !recv_right) || n_sent > h->n_store) return NMPM_ERR_INVALID;
-    if (h->phase_next != 0) {
+    if (h->phase_next != 0 && !h->p2g_early) {
         h->last_error = "nmpm_slab_unpack: must follow nmpm_slab_grid_g2p";
         return NMPM_ERR_INVALID;
     }

@@ -259,8 +259,11 @@ __device__ __forceinline__ bool stencil_of(const float (&x)[D], const MaterialPa
 template <int D, int MODEL>
 __global__ void __launch_bounds__(128) k_p2g_scatter(ParticleStore S, const uint32_t* __restrict__ perm, uint32_t n,
                                                      MaterialParams P, float4* __restrict__ grid,
-                                                     int* __restrict__ error_flag, const uint32_t* __restrict__ gone_keys) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+                                                     int* __restrict__ error_flag, const uint32_t* __restrict__ gone_keys,
+                                                     uint32_t first) {
+    // slots [first, n): `first` > 0 scatters only the tail of the store (slab mode: particles received after the
+    // P2G of the resident ones was already issued)
+    const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (gone_keys && __ldg(gone_keys + i) == kKeyGone) return;  // slab mode between sorts: migrated away
     PState<D> p;

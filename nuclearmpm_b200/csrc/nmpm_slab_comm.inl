@@ -74,6 +74,8 @@ struct nmpm_slab_comm {
     int *d_mine = nullptr, *d_table = nullptr, *h_table = nullptr;
     std::vector<int> boxes;  // world x 6 (lo[3], hi[3]) of the particles of the coming step; empty = unknown
     long long migrated = 0;
+    cudaEvent_t ev_table = nullptr;
+    bool p2g_issued = false;  // the P2G of the coming step is already on the stream (see slab_exchange_migrants)
 };
 
 #define NCCL_TRY(h, expr)                                                                                   \
@@ -92,6 +94,7 @@ static void slab_comm_free(nmpm_sim* h) {
         cudaFree(c->pl_send[s]), cudaFree(c->pl_recv[s]), cudaFree(c->mig_send[s]), cudaFree(c->mig_recv[s]);
     }
     cudaFree(c->d_mine), cudaFree(c->d_table);
+    if (c->ev_table) cudaEventDestroy(c->ev_table);
     if (c->h_table) cudaFreeHost(c->h_table);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     delete c;
@@ -163,14 +166,21 @@ static int slab_exchange_planes(nmpm_sim* h) {
     return NMPM_OK;
 }
 
-static int slab_exchange_migrants(nmpm_sim* h) {
+// `early_p2g`: the coming step is an in-place one inside the same nmpm_slab_step call; its P2G over the resident slots
+// is issued BEFORE the host waits for the table, so the GPU works through it while the host sizes and posts the
+// migrant exchange; the received particles are scattered afterwards (P2G is additive).
+static int slab_exchange_migrants(nmpm_sim* h, bool early_p2g) {
     nmpm_slab_comm* c = h->sc;
     // counts (written by the G2P) + the node box of the coming step, gathered from every rank
     CUDA_TRY(h, cudaMemcpyAsync(c->d_mine + 4, h->d_box + h->box_cur, 6 * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
     NCCL_TRY(h, g_nccl.AllGather(c->d_mine, c->d_table, kTableInts, ncclInt32, c->comm, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(c->h_table, c->d_table, (size_t) c->world * kTableInts * sizeof(int), cudaMemcpyDeviceToHost,
                                 h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // the one host sync of the step
+    CUDA_TRY(h, cudaEventRecord(c->ev_table, h->stream));
+    const size_t first_new = h->n_store;
+    if (early_p2g)
+        if (int rc = slab_p2g_early(h)) return rc;
+    CUDA_TRY(h, cudaEventSynchronize(c->ev_table));  // the one host wait of the step (table + error flag have landed)
     if (int rc = poll_error(h)) return rc;
     const int* t = c->h_table;
     c->boxes.resize((size_t) c->world * 6);
@@ -202,7 +212,12 @@ static int slab_exchange_migrants(nmpm_sim* h) {
         NCCL_TRY(h, g_nccl.GroupEnd());
     }
     c->migrated += (long long) (n_send[0] + n_send[1]);
-    return nmpm_slab_unpack(h, c->mig_recv[0], n_recv[0], c->mig_recv[1], n_recv[1], n_send[0] + n_send[1]);
+    if (int rc = nmpm_slab_unpack(h, c->mig_recv[0], n_recv[0], c->mig_recv[1], n_recv[1], n_send[0] + n_send[1])) return rc;
+    if (early_p2g) {
+        if (int rc = slab_p2g_tail(h, first_new)) return rc;
+        c->p2g_issued = true;
+    }
+    return NMPM_OK;
 }
 
 extern "C" {
@@ -246,6 +261,7 @@ int nmpm_slab_comm_init(nmpm_handle h, const void* unique_id128, int rank, int w
     CUDA_TRY(h, cudaMemset(c->d_mine, 0, kTableInts * sizeof(int)));
     CUDA_TRY(h, cudaMalloc(&c->d_table, (size_t) world * kTableInts * sizeof(int)));
     CUDA_TRY(h, cudaMallocHost(&c->h_table, (size_t) world * kTableInts * sizeof(int)));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&c->ev_table, cudaEventDisableTiming));
     return NMPM_OK;
 }
 
@@ -269,11 +285,15 @@ int nmpm_slab_step(nmpm_handle h, int nsteps) {
     }
     nmpm_slab_comm* c = h->sc;
     for (int s = 0; s < nsteps; ++s) {
-        if (int rc = nmpm_slab_p2g(h)) return rc;
+        if (c->p2g_issued) {
+            c->p2g_issued = false;
+        } else if (int rc = nmpm_slab_p2g(h)) {
+            return rc;
+        }
         if (int rc = slab_exchange_planes(h)) return rc;
         if (int rc = nmpm_slab_grid_g2p(h, c->mig_send[0], c->mig_send[1], c->cap_records, c->d_mine)) return rc;
         c->grid_bounds = c->bounds;  // after this G2P every particle obeys the current boundaries
-        if (int rc = slab_exchange_migrants(h)) return rc;
+        if (int rc = slab_exchange_migrants(h, s + 1 < nsteps && slab_next_step_in_place(h))) return rc;
     }
     return NMPM_OK;
 }
