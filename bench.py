@@ -325,7 +325,7 @@ def main():
     ap.add_argument("--sort-every", type=int, default=4)
     ap.add_argument("--p2g-variant", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--rebalance-every", type=int, default=20, help="multi-GPU: re-balance slab boundaries every k steps")
+    ap.add_argument("--rebalance-every", type=int, default=50, help="multi-GPU: re-balance slab boundaries every k steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
     if args.impl == "reference":

@@ -5,6 +5,7 @@
 // Included at the end of nmpm_api.cu (it needs nmpm_sim and the static step helpers).  NCCL is not a
 // link-time dependency: the symbols are taken with dlopen/dlsym from the libnccl.so.2 the host process
 // already has loaded (torch's), or from an explicit path.
+#include <cstdlib>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -76,6 +77,11 @@ struct nmpm_slab_comm {
     long long migrated = 0;
     cudaEvent_t ev_table = nullptr;
     bool p2g_issued = false;  // the P2G of the coming step is already on the stream (see slab_exchange_migrants)
+    // NMPM_SLAB_TRACE=1: device time of the segments of a free-running step (events, one sync per nmpm_slab_step call)
+    bool trace = false;
+    std::vector<cudaEvent_t> tev;  // 5 per step: start, after P2G, after plane exchange, after G2P, after migrants
+    double tsum[4] = {0, 0, 0, 0};
+    long long tsteps = 0;
 };
 
 #define NCCL_TRY(h, expr)                                                                                   \
@@ -95,6 +101,13 @@ static void slab_comm_free(nmpm_sim* h) {
     }
     cudaFree(c->d_mine), cudaFree(c->d_table);
     if (c->ev_table) cudaEventDestroy(c->ev_table);
+    if (c->trace && c->tsteps)
+        std::fprintf(stderr,
+                     "[nmpm slab trace] rank %d: %lld steps, device ms/step: p2g(+sort,clear) %.3f | plane exchange %.3f | "
+                     "grid_op+g2p %.3f | table+migrants %.3f\n",
+                     c->rank, c->tsteps, c->tsum[0] / c->tsteps, c->tsum[1] / c->tsteps, c->tsum[2] / c->tsteps,
+                     c->tsum[3] / c->tsteps);
+    for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
     if (c->h_table) cudaFreeHost(c->h_table);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     delete c;
@@ -262,6 +275,8 @@ int nmpm_slab_comm_init(nmpm_handle h, const void* unique_id128, int rank, int w
     CUDA_TRY(h, cudaMalloc(&c->d_table, (size_t) world * kTableInts * sizeof(int)));
     CUDA_TRY(h, cudaMallocHost(&c->h_table, (size_t) world * kTableInts * sizeof(int)));
     CUDA_TRY(h, cudaEventCreateWithFlags(&c->ev_table, cudaEventDisableTiming));
+    const char* tr = std::getenv("NMPM_SLAB_TRACE");
+    c->trace = tr && *tr && *tr != '0';
     return NMPM_OK;
 }
 
@@ -284,16 +299,48 @@ int nmpm_slab_step(nmpm_handle h, int nsteps) {
         return NMPM_ERR_INVALID;
     }
     nmpm_slab_comm* c = h->sc;
+    if (c->trace) {
+        while (c->tev.size() < (size_t) 5 * nsteps) {
+            cudaEvent_t e;
+            CUDA_TRY(h, cudaEventCreate(&e));
+            c->tev.push_back(e);
+        }
+    }
+    auto mark = [&](int s, int k) {
+        if (c->trace) cudaEventRecord(c->tev[(size_t) 5 * s + k], h->stream);
+    };
     for (int s = 0; s < nsteps; ++s) {
+        mark(s, 0);
         if (c->p2g_issued) {
             c->p2g_issued = false;
         } else if (int rc = nmpm_slab_p2g(h)) {
             return rc;
         }
+        mark(s, 1);
         if (int rc = slab_exchange_planes(h)) return rc;
+        mark(s, 2);
         if (int rc = nmpm_slab_grid_g2p(h, c->mig_send[0], c->mig_send[1], c->cap_records, c->d_mine)) return rc;
         c->grid_bounds = c->bounds;  // after this G2P every particle obeys the current boundaries
-        if (int rc = slab_exchange_migrants(h, s + 1 < nsteps && slab_next_step_in_place(h))) return rc;
+        mark(s, 3);
+        const bool early = !c->trace && s + 1 < nsteps && slab_next_step_in_place(h);  // the trace keeps segments apart
+        if (int rc = slab_exchange_migrants(h, early)) return rc;
+        mark(s, 4);
+    }
+    if (c->trace) {
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        for (int s = 0; s < nsteps; ++s) {
+            float ms = 0;
+            const cudaEvent_t* e = &c->tev[(size_t) 5 * s];
+            cudaEventElapsedTime(&ms, e[0], e[1]);
+            c->tsum[0] += ms;
+            cudaEventElapsedTime(&ms, e[1], e[2]);
+            c->tsum[1] += ms;
+            cudaEventElapsedTime(&ms, e[2], e[3]);
+            c->tsum[2] += ms;
+            cudaEventElapsedTime(&ms, e[3], e[4]);
+            c->tsum[3] += ms;
+        }
+        c->tsteps += nsteps;
     }
     return NMPM_OK;
 }

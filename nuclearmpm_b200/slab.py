@@ -194,6 +194,7 @@ class SlabSimulation:
     (src/nclr.h:74-78) plus the process group.  Every rank passes the SAME global particle arrays."""
 
     MIN_WIDTH = 4
+    REBALANCE_TOL = 0.03  # relative load deviation below which the slab boundaries stay where they are
 
     def __init__(self, particles, model, res=64, dt=1e-4, E=1e4, nu=0.2, gravity=-100.0, *, group=None, device=0,
                  engine_factory=None, slack=0.5, rebalance_every=0, max_shift=2, bounds=None, native=None, **state):
@@ -313,6 +314,13 @@ class SlabSimulation:
         e.histogram(self.hist)
         d.all_reduce(self.hist, group=self.group)
         hist = self.hist.cpu().numpy()
+        # hysteresis: a boundary move makes up to max_shift planes of particles migrate in one step; leave slabs that
+        # are within REBALANCE_TOL of the mean load alone
+        cum = np.concatenate([[0], np.cumsum(hist, dtype=np.int64)])
+        loads = np.diff(cum[np.asarray(self.bounds)])
+        mean = max(1.0, float(cum[-1]) / self.world)
+        if float(np.abs(loads - mean).max()) <= self.REBALANCE_TOL * mean:
+            return
         target = balanced_bounds(hist, self.world, self.MIN_WIDTH)
         new = limited_shift(self.bounds, target, self.max_shift, self.MIN_WIDTH)
         if new != self.bounds:
