@@ -30,6 +30,8 @@
 #include <sstream>
 #include <string>
 #include <unordered_map>
+#include <exception>
+#include <thread>
 #include <vector>
 
 #include "nclr.h"
@@ -244,12 +246,14 @@ struct Scene {
 
 // advances every scene in lockstep: each advance() only enqueues work on that scene's CUDA stream, so the
 // small per-scene kernels of all scenes overlap on the GPU; snapshots synchronise one scene at a time
-static void run_scenes(std::vector<Scene> &scenes) {
+// Scenes are independent: with more than one scene they are spread over host threads (a 1 250-particle step is a
+// ~10 us graph launch, so one thread issuing 64 scenes is launch-bound, and the text snapshots are host work too).
+static void run_scene_range(std::vector<Scene> &scenes, size_t first, size_t stride) {
     int max_steps = 0;
-    for (auto &s : scenes) max_steps = std::max(max_steps, s.cfg.steps);
-    std::cout << "Running simulation" << std::endl;
+    for (size_t k = first; k < scenes.size(); k += stride) max_steps = std::max(max_steps, scenes[k].cfg.steps);
     for (int step = 0; step < max_steps; ++step) {
-        for (auto &s : scenes) {
+        for (size_t k = first; k < scenes.size(); k += stride) {
+            auto &s = scenes[k];
             if (step >= s.cfg.steps || !s.cfg.dump) continue;
             dump_particles(s.tmp, step, s.cfg, s.sim->mu_0, s.sim->lambda_0, s.sim->particles());
             if (step > 0) dump_cells(s.tmp, step, s.sim->grid());
@@ -257,10 +261,33 @@ static void run_scenes(std::vector<Scene> &scenes) {
                 dump_cells(s.tmp, step,
                            std::vector<nclr::Cell<2>>((kGridResolution + 1) * (kGridResolution + 1), nclr::Cell<2>()));
         }
-        for (auto &s : scenes)
-            if (step < s.cfg.steps) s.sim->advance();
+        for (size_t k = first; k < scenes.size(); k += stride)
+            if (step < scenes[k].cfg.steps) scenes[k].sim->advance();
     }
-    for (auto &s : scenes) s.sim->synchronize();
+    for (size_t k = first; k < scenes.size(); k += stride) scenes[k].sim->synchronize();
+}
+
+static void run_scenes(std::vector<Scene> &scenes) {
+    std::cout << "Running simulation" << std::endl;
+    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nthreads = std::min({scenes.size(), hw, size_t(16)});
+    if (nthreads <= 1) {
+        run_scene_range(scenes, 0, 1);
+    } else {
+        std::vector<std::thread> pool;
+        std::vector<std::exception_ptr> errors(nthreads);
+        for (size_t t = 0; t < nthreads; ++t)
+            pool.emplace_back([&scenes, &errors, t, nthreads] {
+                try {
+                    run_scene_range(scenes, t, nthreads);
+                } catch (...) {
+                    errors[t] = std::current_exception();
+                }
+            });
+        for (auto &th : pool) th.join();
+        for (auto &e : errors)
+            if (e) std::rethrow_exception(e);
+    }
     std::cout << "Simulation done" << std::endl;
 }
 

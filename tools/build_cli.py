@@ -23,7 +23,7 @@ def build(force: bool = False) -> Path:
     EXE.parent.mkdir(parents=True, exist_ok=True)
     # $ORIGIN-relative rpath: the binary finds libnmpm.so wherever the repo snapshot lands (GPU box)
     subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", f"-I{ROOT / 'include'}", str(SRC), "-o", str(EXE),
-                    f"-L{LIBDIR}", "-lnmpm", "-Wl,-rpath,$ORIGIN/../../nuclearmpm_b200/lib"], check=True)
+                    f"-L{LIBDIR}", "-lnmpm", "-pthread", "-Wl,-rpath,$ORIGIN/../../nuclearmpm_b200/lib"], check=True)
     return EXE
 
 
