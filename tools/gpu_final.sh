@@ -27,3 +27,4 @@ timeout 900 ncu --set full --clock-control none -k regex:'k_grid_op|k_clear_box|
   -f -o $out/prof_cfg4_small python tools/profile_step.py --workload cfg4 --warmup 28 --steps 4 --sort-every 4 >> $out/ncu_full.log 2>&1
 tail -2 $out/ncu_full.log
 ls -la $out | head -30
+timeout 600 python tools/bench_cfg5.py > $out/cfg5.json 2> $out/cfg5.err; echo "cfg5 rc=$?"; cat $out/cfg5.json
