@@ -346,6 +346,46 @@ def test_full_size_properties_config2(model):
     assert np.isfinite(after["x"]).all()
 
 
+def test_full_size_properties_config4():
+    """BASELINE config 4 size (256^3 = 16.8 M snow particles, 512^3 grid; the bench workload and the only size at
+    which the three-stream P2G (variant 4) is the default): mass and momentum conservation on the post-P2G grid of an
+    in-place (not re-binned) step, |grid v| <= vmax, displacement <= 0.9 dx, Jp = 0.6 after step 1 (Q1), and the
+    default path against the plain column-lane kernel (variant 3) after 6 steps."""
+    x = nm.cube(3, 256, 0.25, 0.5)
+    n = len(x)
+    sim = nm.MPMSimulation(x, co.SNOW, 512)          # auto: variant 4, sort cadence 4
+    sim.advance(1)
+    assert (sim.particles()["Jp"] == np.float32(0.6)).all()
+    sim.advance(1)                                    # step 2 done; step 3 (index 2) is an in-place step
+    before = sim.particles()
+    sim.phase(0)
+    gv, gm = sim.grid()
+    assert np.isclose(gm.astype(np.float64).sum(), float(n), rtol=1e-6)
+    mom = before["v"].astype(np.float64).sum(0)
+    assert np.allclose(gv.astype(np.float64).sum(0), mom, rtol=1e-4, atol=1e-6 * n)
+    del gv, gm
+    sim.phase(1)
+    gv, gm = sim.grid()
+    vmax = np.float32((1.0 / 512) * 0.9 / 1e-4)
+    assert np.abs(gv).max() <= vmax
+    del gv, gm
+    sim.phase(2)
+    after = sim.particles()
+    assert np.isfinite(after["x"]).all()
+    assert np.abs(after["x"] - before["x"]).max() <= 0.9 / 512 * 1.0001
+    del before
+    sim.advance(3)                                    # 6 steps in all
+    got = sim.particles()
+    del sim
+    ref_sim = nm.MPMSimulation(x, co.SNOW, 512, p2g_variant=3)
+    ref_sim.advance(6)
+    ref = ref_sim.particles()
+    # same physics up to the summation order of the reductions; 3D snow amplifies rounding from step 4 on (Q1)
+    dx = np.abs(got["x"] - ref["x"]).max(axis=1)
+    assert np.quantile(dx, 0.999) <= 1e-5 and dx.max() <= 2.0 / 512, (float(np.quantile(dx, 0.999)), float(dx.max()))
+    assert np.median(np.abs(got["v"] - ref["v"])) <= 1e-4 * max(1.0, float(np.abs(ref["v"]).max()))
+
+
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["snow_F", "snow_Fprime_q1", "snow_Fprime_phys", "jelly_rank2", "liquid_diag",
                                   "general", "step0", "scaled"])
