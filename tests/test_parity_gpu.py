@@ -350,7 +350,7 @@ def test_full_size_properties_config4():
     """BASELINE config 4 size (256^3 = 16.8 M snow particles, 512^3 grid; the bench workload and the only size at
     which the three-stream P2G (variant 4) is the default): mass and momentum conservation on the post-P2G grid of an
     in-place (not re-binned) step, |grid v| <= vmax, displacement <= 0.9 dx, Jp = 0.6 after step 1 (Q1), and the
-    default path against the plain column-lane kernel (variant 3) after 6 steps."""
+    default path against the plain column-lane kernel (variant 3) after 3 steps."""
     x = nm.cube(3, 256, 0.25, 0.5)
     n = len(x)
     sim = nm.MPMSimulation(x, co.SNOW, 512)          # auto: variant 4, sort cadence 4
@@ -373,17 +373,15 @@ def test_full_size_properties_config4():
     after = sim.particles()
     assert np.isfinite(after["x"]).all()
     assert np.abs(after["x"] - before["x"]).max() <= 0.9 / 512 * 1.0001
-    del before
-    sim.advance(3)                                    # 6 steps in all
-    got = sim.particles()
-    del sim
+    del before, sim
+    # three steps (one re-binned, two in place) of the default path against the plain column-lane kernel: same physics
+    # up to the summation order of the reductions.  Three steps only: 3D snow decorrelates at step 4 (Q1, SURVEY.md
+    # 4.3 - measured here: after 6 steps 0.1 % of the particles are more than a cell apart between the two variants)
     ref_sim = nm.MPMSimulation(x, co.SNOW, 512, p2g_variant=3)
-    ref_sim.advance(6)
+    ref_sim.advance(3)
     ref = ref_sim.particles()
-    # same physics up to the summation order of the reductions; 3D snow amplifies rounding from step 4 on (Q1)
-    dx = np.abs(got["x"] - ref["x"]).max(axis=1)
-    assert np.quantile(dx, 0.999) <= 1e-5 and dx.max() <= 2.0 / 512, (float(np.quantile(dx, 0.999)), float(dx.max()))
-    assert np.median(np.abs(got["v"] - ref["v"])) <= 1e-4 * max(1.0, float(np.abs(ref["v"]).max()))
+    assert np.abs(after["x"] - ref["x"]).max() <= 1e-5
+    assert np.abs(after["v"] - ref["v"]).max() <= 2e-3 * max(1.0, float(np.abs(ref["v"]).max()))
 
 
 # ------------------------------------------------------------------------------------------
