@@ -2,6 +2,7 @@
 // the per-step launch sequence.  No CPU fallback: without a usable CUDA device every compute entry
 // point returns NMPM_ERR_NO_DEVICE / NMPM_ERR_CUDA.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -65,6 +66,7 @@ struct nmpm_sim {
     std::vector<std::array<int, 5>> dirty_rects;    // slab mode: in-plane rectangles written by the native ghost exchange
     struct nmpm_slab_comm* sc = nullptr;            // native slab step (nmpm_slab_comm.inl)
     bool box_valid = false;   // box[box_cur] describes store[cur]
+    bool local_reorder = true;  // in-place G2P re-groups each warp's 32 slots by cell key (NMPM_LOCAL_REORDER=0: off)
     bool p2g_early = false;   // slab mode: the in-place P2G of the coming step was issued before the migrants arrived
     bool grid_valid = false;  // false until the first p2g: the reference's grid() is empty (src/solver.cpp:52-57)
 
@@ -229,6 +231,7 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
         return NMPM_ERR_INVALID;
     }
     h->dim = dim, h->model = model, h->res = res, h->n = n;
+    if (const char* lr = std::getenv("NMPM_LOCAL_REORDER")) h->local_reorder = (*lr != '0');
     h->n_store = n;
     h->slab = h->opt.slab_x1 > 0;
     h->cap = n;
@@ -585,7 +588,7 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
     k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + box_next);
     NMPM_DISPATCH(h, (k_g2p_gather<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(
                          S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error, mig,
-                         h->d_box_partial, gone_keys)));
+                         h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0)));
     {   // warps of the launch above (128-thread CTAs): every one of them wrote a partial box
         const uint32_t nwarps = blocks_for(n, 128) * 4u - ((blocks_for(n, 128) * 128u - n) / 32u);
         const unsigned rb = nwarps / 1024 + 1 < 148u ? nwarps / 1024 + 1 : 148u;

@@ -400,7 +400,8 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
                                                     uint32_t n, MaterialParams P, const float4* __restrict__ grid,
                                                     uint32_t* __restrict__ keys_out, int tiles_per_axis,
                                                     int* __restrict__ error_flag, MigrateArgs mig,
-                                                    int* __restrict__ box_partial, const uint32_t* __restrict__ gone_keys) {
+                                                    int* __restrict__ box_partial, const uint32_t* __restrict__ gone_keys,
+                                                    int local_reorder) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // slab mode between sorts: a slot whose particle migrated away is skipped (its key stays kKeyGone)
     const bool mine = i < n && !(gone_keys && __ldg(gone_keys + i) == kKeyGone);
@@ -518,18 +519,7 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
         }
     }
     g2p_update<D, MODEL>(p, Cn, vn, P);
-    store_state<D>(T, i, p);
-    float2 mv = make_float2(0.0f, 0.0f);
-    uint32_t pid = 0;
-    if (perm || mig.left) {
-        mv = __ldg(S.mv + src);
-        pid = __ldg(S.id + src);
-    }
-    if (perm) {
-        T.mv[i] = mv;
-        T.id[i] = pid;
-    }
-    {   // bin the advected particle for the NEXT step: cell key (if that step sorts), slab owner, node box
+    {   // bin the advected particle for the NEXT step: cell key, slab owner, node box
         int b[D];
         bool bad = false;
 #pragma unroll
@@ -540,6 +530,37 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
         }
         // an out-of-grid position is flagged by the next step's P2G/G2P (that is when the reference throws)
         uint32_t key = bad ? kKeyOutOfGrid : cell_key<D>(b, tiles_per_axis);
+        // In-place steps (no re-binning this step, single GPU): the warp writes its 32 particles back ORDERED BY THEIR NEW
+        // CELL KEY instead of slot by slot.  Between two radix sorts the particles of a cell drift into 2-3 neighbouring
+        // cells and interleave (A B A A C B ...): P2G then meets one run per fragment, and every run costs 27
+        // lane-reductions.  Re-grouping inside the warp's own 32 slots needs no extra pass and no shared memory.
+        const bool reorder = local_reorder && !perm && !mig.left && !gone_keys;  // warp-uniform (kernel arguments)
+        float2 mv = make_float2(0.0f, 0.0f);
+        uint32_t pid = 0;
+        if (perm || mig.left || reorder) {
+            mv = __ldg(S.mv + src);
+            pid = __ldg(S.id + src);
+        }
+        uint32_t dst = i;
+        if (reorder) {
+            const int lane = threadIdx.x & 31;
+            const unsigned peers = __match_any_sync(live, key);  // lanes whose particle lands in the same cell
+            const unsigned leaders = __ballot_sync(live, lane == __ffs(peers) - 1);
+            int before = 0;  // particles of this warp in cells with a smaller key
+            for (unsigned m = leaders; m; m &= m - 1) {
+                const int L = __ffs(m) - 1;
+                const uint32_t kL = __shfl_sync(live, key, L);
+                const int sz = __popc(__shfl_sync(live, peers, L));
+                if (kL < key) before += sz;
+            }
+            dst = (i - lane) + (uint32_t) (before + __popc(peers & ((1u << lane) - 1u)));
+            __syncwarp(live);  // T == S: every lane has read its old slot (state, mass/volume, id) before any is overwritten
+        }
+        store_state<D>(T, dst, p);
+        if (perm || reorder) {
+            T.mv[dst] = mv;
+            T.id[dst] = pid;
+        }
         bool gone = false;
         if (mig.left && !bad && (b[0] < mig.x0 || b[0] >= mig.x1)) {
             const int side = (b[0] < mig.x0) ? 0 : 1;
@@ -552,7 +573,8 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
                 atomicExch(mig.counts + 3, 1);  // send buffer overflow: fatal for the caller
             }
         }
-        if (keys_out) keys_out[i] = key;
+        (void) gone;
+        if (keys_out) keys_out[dst] = key;
 #pragma unroll
         for (int d = 0; d < D; ++d) b[d] = min(max(b[d], 0), P.res - 2);
         // migrants stay in the sender's box: the box table of the slab protocol must cover them until they are unpacked
