@@ -418,6 +418,15 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
     const uint32_t src = perm ? __ldg(perm + i) : i;
     PState<D> p;
     load_for_g2p<D>(S, src, p);
+    // mass/volume and id travel with the particle whenever it changes slot (re-binned write, migration, warp-local
+    // re-grouping); loaded here, with the state, so that their latency hides behind the gather
+    const bool reorder = local_reorder && !perm && !mig.left && !gone_keys;  // warp-uniform (kernel arguments)
+    float2 mv = make_float2(0.0f, 0.0f);
+    uint32_t pid = 0;
+    if (perm || mig.left || reorder) {
+        mv = __ldg(S.mv + src);
+        pid = __ldg(S.id + src);
+    }
     int base[D];
     float fx[D], w[D][3];
     if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
@@ -534,15 +543,15 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
         // CELL KEY instead of slot by slot.  Between two radix sorts the particles of a cell drift into 2-3 neighbouring
         // cells and interleave (A B A A C B ...): P2G then meets one run per fragment, and every run costs 27
         // lane-reductions.  Re-grouping inside the warp's own 32 slots needs no extra pass and no shared memory.
-        const bool reorder = local_reorder && !perm && !mig.left && !gone_keys;  // warp-uniform (kernel arguments)
-        float2 mv = make_float2(0.0f, 0.0f);
-        uint32_t pid = 0;
-        if (perm || mig.left || reorder) {
-            mv = __ldg(S.mv + src);
-            pid = __ldg(S.id + src);
-        }
         uint32_t dst = i;
+        bool moved = false;
+        // nothing to do for a warp whose keys are already non-decreasing along the lanes (calm scenes, fresh sorts)
         if (reorder) {
+            const int lane = threadIdx.x & 31;
+            const uint32_t prev = __shfl_up_sync(live, key, 1);
+            moved = __any_sync(live, lane > 0 && ((live >> (lane - 1)) & 1u) && prev > key);
+        }
+        if (moved) {
             const int lane = threadIdx.x & 31;
             const unsigned peers = __match_any_sync(live, key);  // lanes whose particle lands in the same cell
             const unsigned leaders = __ballot_sync(live, lane == __ffs(peers) - 1);
@@ -557,7 +566,7 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
             __syncwarp(live);  // T == S: every lane has read its old slot (state, mass/volume, id) before any is overwritten
         }
         store_state<D>(T, dst, p);
-        if (perm || reorder) {
+        if (perm || moved) {
             T.mv[dst] = mv;
             T.id[dst] = pid;
         }
