@@ -418,15 +418,7 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
     const uint32_t src = perm ? __ldg(perm + i) : i;
     PState<D> p;
     load_for_g2p<D>(S, src, p);
-    // mass/volume and id travel with the particle whenever it changes slot (re-binned write, migration, warp-local
-    // re-grouping); loaded here, with the state, so that their latency hides behind the gather
     const bool reorder = local_reorder && !perm && !mig.left && !gone_keys;  // warp-uniform (kernel arguments)
-    float2 mv = make_float2(0.0f, 0.0f);
-    uint32_t pid = 0;
-    if (perm || mig.left || reorder) {
-        mv = __ldg(S.mv + src);
-        pid = __ldg(S.id + src);
-    }
     int base[D];
     float fx[D], w[D][3];
     if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
@@ -550,6 +542,14 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
             const int lane = threadIdx.x & 31;
             const uint32_t prev = __shfl_up_sync(live, key, 1);
             moved = __any_sync(live, lane > 0 && ((live >> (lane - 1)) & 1u) && prev > key);
+        }
+        // mass/volume and id travel with the particle whenever it changes slot (re-binned write, migration, re-grouping).
+        // (Loading them at the top of the kernel to hide their latency costs more in register pressure than it saves.)
+        float2 mv = make_float2(0.0f, 0.0f);
+        uint32_t pid = 0;
+        if (perm || mig.left || moved) {
+            mv = __ldg(S.mv + src);
+            pid = __ldg(S.id + src);
         }
         if (moved) {
             const int lane = threadIdx.x & 31;
