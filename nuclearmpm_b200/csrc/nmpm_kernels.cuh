@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
     const uint32_t src = perm ? __ldg(perm + i) : i;
     PState<D> p;
     load_for_g2p<D>(S, src, p);
-    const bool reorder = local_reorder && !perm && !mig.left && !gone_keys;  // warp-uniform (kernel arguments)
+    const bool reorder = local_reorder && !mig.left && !gone_keys;  // warp-uniform (kernel arguments); single GPU only
     int base[D];
     float fx[D], w[D][3];
     if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
@@ -531,10 +531,10 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
         }
         // an out-of-grid position is flagged by the next step's P2G/G2P (that is when the reference throws)
         uint32_t key = bad ? kKeyOutOfGrid : cell_key<D>(b, tiles_per_axis);
-        // In-place steps (no re-binning this step, single GPU): the warp writes its 32 particles back ORDERED BY THEIR NEW
-        // CELL KEY instead of slot by slot.  Between two radix sorts the particles of a cell drift into 2-3 neighbouring
-        // cells and interleave (A B A A C B ...): P2G then meets one run per fragment, and every run costs 27
-        // lane-reductions.  Re-grouping inside the warp's own 32 slots needs no extra pass and no shared memory.
+        // Single GPU: the warp writes its 32 particles back GROUPED BY THEIR NEW CELL instead of slot by slot.  Between
+        // two radix sorts the particles of a cell drift into 2-3 neighbouring cells and interleave (A B A A C B ...): P2G
+        // then meets one run per fragment, and every run costs 27 lane-reductions.  Re-grouping inside the warp's own 32
+        // slots needs no extra pass and no shared memory (on a re-binned step it is free of extra traffic as well).
         uint32_t dst = i;
         bool moved = false;
         // nothing to do for a warp whose keys are already non-decreasing along the lanes (calm scenes, fresh sorts)
@@ -554,15 +554,21 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
         if (moved) {
             const int lane = threadIdx.x & 31;
             const unsigned peers = __match_any_sync(live, key);  // lanes whose particle lands in the same cell
-            const unsigned leaders = __ballot_sync(live, lane == __ffs(peers) - 1);
-            int before = 0;  // particles of this warp in cells with a smaller key
-            for (unsigned m = leaders; m; m &= m - 1) {
-                const int L = __ffs(m) - 1;
-                const uint32_t kL = __shfl_sync(live, key, L);
-                const int sz = __popc(__shfl_sync(live, peers, L));
-                if (kL < key) before += sz;
+            // cells in the order of their first particle: `before` = lanes whose cell's first lane precedes mine's,
+            // counted with five ballots (one per bit of the 5-bit first-lane index, most significant first)
+            const int leader = __ffs(peers) - 1;
+            unsigned lt = 0u, eq = live;
+#pragma unroll
+            for (int bit = 4; bit >= 0; --bit) {
+                const unsigned ones = __ballot_sync(live, (leader >> bit) & 1);
+                if ((leader >> bit) & 1) {
+                    lt |= eq & ~ones;
+                    eq &= ones;
+                } else {
+                    eq &= ~ones;
+                }
             }
-            dst = (i - lane) + (uint32_t) (before + __popc(peers & ((1u << lane) - 1u)));
+            dst = (i - lane) + (uint32_t) (__popc(lt) + __popc(peers & ((1u << lane) - 1u)));
             __syncwarp(live);  // T == S: every lane has read its old slot (state, mass/volume, id) before any is overwritten
         }
         store_state<D>(T, dst, p);

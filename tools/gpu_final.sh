@@ -23,8 +23,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --c
   python tools/profile_step.py --workload cfg4 --warmup 28 --steps 8 --sort-every 4 > $out/ncu_launches.log 2>&1
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_p2g|k_g2p_gather' -s 56 -c 8 \
   -f -o $out/prof_cfg4_late python tools/profile_step.py --workload cfg4 --warmup 28 --steps 6 --sort-every 4 > $out/ncu_full.log 2>&1
-[ -z "$light" ] && timeout 900 ncu --set full --clock-control none -k regex:'k_grid_op|k_clear_box|sort_scatter|sort_hist' -s 70 -c 6 \
+if [ -z "$light" ]; then timeout 900 ncu --set full --clock-control none -k regex:'k_grid_op|k_clear_box|sort_scatter|sort_hist' -s 70 -c 6 \
   -f -o $out/prof_cfg4_small python tools/profile_step.py --workload cfg4 --warmup 28 --steps 4 --sort-every 4 >> $out/ncu_full.log 2>&1
+fi
 tail -2 $out/ncu_full.log
 ls -la $out | head -30
-[ -z "$light" ] && timeout 600 python tools/bench_cfg5.py > $out/cfg5.json 2> $out/cfg5.err; echo "cfg5 rc=$?"; cat $out/cfg5.json
+if [ -z "$light" ]; then timeout 600 python tools/bench_cfg5.py > $out/cfg5.json 2> $out/cfg5.err; echo "cfg5 rc=$?"; cat $out/cfg5.json
+fi
