@@ -1,4 +1,11 @@
-// K2 (variant 2): P2G by warp-level segmented reduction over cell-sorted particles.
+// K2: P2G by warp-level segmented reduction over cell-sorted particles.  Three kernels share the scheme
+// (phase A: lane = particle, packet to shared memory; phase B: lanes = stencil nodes walk the packets, accumulate a
+// run of particles of one cell in registers, one vector reduction per node and run):
+//   variant 2  k_p2g_cell<D,MODEL>    lane = stencil node, particle pairs in packed fp32x2   (2D default; 3D baseline)
+//   variant 3  k_p2g_cols<MODEL>      three 9-lane groups, lane = stencil column (j,k), per-column packets   (3D default)
+//   variant 4  k_p2g_streams<MODEL>   variant 3 over three particle streams per warp   (3D default from 8 Mi particles)
+//
+// Variant 2:
 //
 // Reference: p2g() + compute_fused_momentum() + first_piola_kirchoff_stress(), src/nclr.h:104-165,
 // 313-337 — there a serial loop doing 3^dim read-modify-writes per particle.  Here:
