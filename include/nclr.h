@@ -30,6 +30,7 @@
 #include <cassert>
 #include <cmath>
 #include <cstddef>
+#include <cstdio>
 #include <cstdint>
 #include <iomanip>
 #include <iostream>
@@ -182,6 +183,38 @@ namespace nclr {
     // Eigen's default IOFormat (src/solver.cpp:71 streams x, v, F, C with it)
     template<typename T, int R, int C>
     inline std::ostream &operator<<(std::ostream &os, const Mat<T, R, C> &a) {
+        // Fast path (the dump writers call this millions of times): a stream in the default state prints a float like
+        // printf("%.*g", precision, double(x)); coefficients are formatted once into stack buffers and written
+        // right-aligned to the widest one.  Any other stream state takes the generic two-pass path below.
+        if constexpr (std::is_floating_point_v<T>) {
+            const auto fl = os.flags();
+            const bool plain = !(fl & std::ios_base::floatfield) && !(fl & (std::ios_base::showpos | std::ios_base::showpoint |
+                                                                            std::ios_base::uppercase)) &&
+                               (fl & std::ios_base::adjustfield) != std::ios_base::left &&
+                               (fl & std::ios_base::adjustfield) != std::ios_base::internal && os.fill() == ' ' &&
+                               os.width() == 0 && os.getloc() == std::locale::classic();
+            if (plain) {
+                char buf[R * C][40];
+                int len[R * C];
+                int width = 0;
+                const int prec = os.precision() > 0 ? int(os.precision()) : (os.precision() == 0 ? 1 : 6);
+                for (int k = 0; k < R * C; ++k) {
+                    len[k] = std::snprintf(buf[k], sizeof buf[k], "%.*g", prec, double(a.m[k]));
+                    width = std::max(width, len[k]);
+                }
+                static const char spaces[41] = "                                        ";
+                for (int i = 0; i < R; ++i) {
+                    if (i) os.put('\n');
+                    for (int j = 0; j < C; ++j) {
+                        if (j) os.put(' ');
+                        const int k = i + j * R;
+                        os.write(spaces, width - len[k]);
+                        os.write(buf[k], len[k]);
+                    }
+                }
+                return os;
+            }
+        }
         std::size_t width = 0;
         for (int k = 0; k < R * C; ++k) {
             std::ostringstream ss;

@@ -32,7 +32,8 @@ def test_matrix_stream_format_matches_eigen_default(tmp_path):
     # Eigen IOFormat(): stream precision 6, ' ' between columns, '\n' between rows, every coefficient
     # right-aligned to the widest one of the matrix
     assert out == ("0.4\n0.6\n--\n1 0\n0 1\n--\n 1.5   -2\n   3 4.25\n--\n1 0 0\n0 1 0\n0 0 0\n--\n"
-                   "3846.15 5769.23\n--\n0.123457\n0.123457\n0.123457\n")
+                   "3846.15 5769.23\n--\n0.123457\n0.123457\n0.123457\n"
+                   "fast-path mismatches: 0\n")
 
 
 @pytest.mark.skipif(not (REF / "src" / "solver.cpp").exists(), reason="reference tree not present (GPU box)")
