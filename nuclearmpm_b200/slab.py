@@ -57,6 +57,15 @@ def balanced_bounds(hist: np.ndarray, world: int, min_width: int = 4) -> list[in
     return b
 
 
+def load_imbalance(hist: np.ndarray, bounds: list[int]) -> float:
+    """Largest relative deviation of a slab's particle count from the mean, for boundaries `bounds` over the per-plane
+    histogram `hist` (0 = perfectly balanced)."""
+    cum = np.concatenate([[0], np.cumsum(hist, dtype=np.int64)])
+    loads = np.diff(cum[np.asarray(bounds)])
+    mean = max(1.0, float(cum[-1]) / (len(bounds) - 1))
+    return float(np.abs(loads - mean).max()) / mean
+
+
 def limited_shift(old: list[int], new: list[int], max_shift: int, min_width: int = 4) -> list[int]:
     """Move every interior boundary towards `new` by at most `max_shift` planes, keeping min widths."""
     out = [old[0]]
@@ -316,10 +325,7 @@ class SlabSimulation:
         hist = self.hist.cpu().numpy()
         # hysteresis: a boundary move makes up to max_shift planes of particles migrate in one step; leave slabs that
         # are within REBALANCE_TOL of the mean load alone
-        cum = np.concatenate([[0], np.cumsum(hist, dtype=np.int64)])
-        loads = np.diff(cum[np.asarray(self.bounds)])
-        mean = max(1.0, float(cum[-1]) / self.world)
-        if float(np.abs(loads - mean).max()) <= self.REBALANCE_TOL * mean:
+        if load_imbalance(hist, self.bounds) <= self.REBALANCE_TOL:
             return
         target = balanced_bounds(hist, self.world, self.MIN_WIDTH)
         new = limited_shift(self.bounds, target, self.max_shift, self.MIN_WIDTH)

@@ -111,3 +111,17 @@ def test_slab_protocol_matches_single_domain_oracle(dim, model, world, rebalance
           "final counts", [i["counts"][-1] for i in infos])
     if rebalance or dim == 2:
         assert sum(i["migrated"] for i in infos) > 0  # the migration path was exercised
+
+
+def test_rebalance_hysteresis_measure():
+    """load_imbalance drives the re-balancing hysteresis (SlabSimulation.REBALANCE_TOL): balanced boundaries read 0,
+    a slab holding 10 % more than the mean reads 0.1, and balanced_bounds brings a skewed split back under it."""
+    from nuclearmpm_b200.slab import SlabSimulation, balanced_bounds, load_imbalance
+    hist = np.zeros(65, np.int64)
+    hist[16:48] = 100                                   # 32 planes of 100 particles
+    assert load_imbalance(hist, [0, 32, 65]) == 0.0
+    assert abs(load_imbalance(hist, [0, 24, 40, 65]) - 0.5) < 1e-12   # 800 / 1600 / 800 against a mean of 1066.67
+    skew = [0, 30, 65]                                  # 1400 vs 1800: 12.5 % off the mean of 1600
+    assert abs(load_imbalance(hist, skew) - 0.125) < 1e-12
+    assert load_imbalance(hist, skew) > SlabSimulation.REBALANCE_TOL
+    assert load_imbalance(hist, balanced_bounds(hist, 2)) <= SlabSimulation.REBALANCE_TOL
