@@ -198,7 +198,10 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL writes its version banner / debug lines to stdout by default: keep stdout for the ONE JSON line
+        # NCCL writes its version banner / debug lines to stdout by default: keep stdout for the ONE JSON line.
+        # (NCCL_DEBUG_FILE is honoured only above the VERSION level, so VERSION is raised to WARN.)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
