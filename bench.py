@@ -149,6 +149,18 @@ def cpu_sample(workload: str, budget_s: float):
     return xs, model, res, dim, what
 
 
+def host_cpu():
+    model = "unknown"
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"model": model, "cores_total": os.cpu_count()}
+
+
 def cpu_reference_rate(workload: str, steps: int, warmup: int, budget_s: float = 20.0):
     from oracle import cpu_oracle as co
     kind = "ref_fast" if co.available("ref_fast") else "port"
@@ -159,6 +171,7 @@ def cpu_reference_rate(workload: str, steps: int, warmup: int, budget_s: float =
     t = sim.time_advance(steps)
     rate = len(xs) * steps / t
     return dict(value=rate, unit="particle-steps/s", cores=1, kind="reference" if kind == "ref_fast" else "port",
+                host=host_cpu(),
                 sample=f"{what}; {steps} advance() steps in {t:.2f} s on 1 host core "
                        f"({'reference nclr.h, -Ofast, Eigen stand-in' if kind == 'ref_fast' else 'oracle port, -O2'})"), t
 
@@ -263,7 +276,7 @@ def run_gpu(args):
     dom_ms = phases[dom + "_ms"]
     achieved = ab[dom] * n_total / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(dom, n_total) if dim == 3 else None, "peak_source": peak_src,
+                "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": ncu_traffic(dom, n_total) if dim == 3 else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_particle": ab[dom],
                 "other": {k: {"ms": phases[k + "_ms"],
                               "achieved_GBps": ab[k] * n_total / (phases[k + "_ms"] * 1e-3) / 1e9 if phases[k + "_ms"] > 0 else 0.0}
