@@ -1,7 +1,8 @@
 """Print the measured one-step parity errors of the CUDA path against the golden vectors
-(teacher-forced from reference states) next to the stated tolerances.  GPU box only.
+(teacher-forced from reference states) next to the stated tolerances.  GPU box only; test infrastructure (it uses
+the oracle for the cell keys), hence under tests/.
 
-    python tools/parity_report.py > profiles/rNN_parity.md
+    python tests/parity_report.py > profiles/rNN_parity.md
 """
 import sys
 from pathlib import Path
@@ -10,7 +11,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, str(ROOT / "tests"))
+sys.path.insert(0, str(ROOT / "tests"))  # conftest helpers / test_parity_gpu tolerances
 import nuclearmpm_b200 as nm  # noqa: E402
 from oracle import cpu_oracle as co  # noqa: E402
 from test_parity_gpu import TOL_C, TOL_F, TOL_GRID_V, TOL_JP, TOL_V, TOL_X  # noqa: E402
