@@ -127,26 +127,24 @@ def ncu_traffic(kernel: str, n_particles: float):
 # ----------------------------------------------------------------------------------------------
 # CPU baseline: the reference's own advance() (oracle/_ref, -Ofast build) or the oracle port
 # ----------------------------------------------------------------------------------------------
-def cpu_sample(workload: str, budget_s: float):
-    """A bounded sample of `workload` for the CPU: same material, spacing, dt and grid; fewer particles."""
+def cpu_sample(workload: str):
+    """What the CPU arm times for `workload`.
+
+    Every workload except cfg4 is run in full.  cfg4 (16.8 M particles on 513^3 nodes) costs the single-threaded
+    reference ~25 s per step, so K steps of it do not fit a bench run; its sample is the SAME scene at half the
+    linear resolution — cube<3>(128, 0.25, 0.5) on a 256^3 grid: same material, dt, particles per cell (8) and
+    grid nodes per particle (8.1 vs 8.05), i.e. the same mix of per-particle work (p2g/g2p + SVD) and per-node work
+    (the reference re-allocates and walks the dense grid every step, src/nclr.h:105-109,263-282).  A sub-block on
+    the full 513^3 grid (round 1) over-weights the per-node work and under-states the reference several times.
+    `--impl reference` additionally times real full-scene steps (`full_scene`)."""
     import nuclearmpm_b200 as nm
     x, model, res, desc = scene(workload)
     dim = x.shape[1]
     if workload == "cfg4":
-        m = 128 if budget_s >= 8 else 64
-        xs = nm.cube(3, m, 0.25, 0.25 + (m - 1) * (0.25 / 255))
-        what = f"cube<3>({m}) sub-block of cfg4 ({len(xs)} p, same spacing, 512^3 grid)"
-    elif workload == "snow128":
-        m = 64
-        xs = nm.cube(3, m, 0.2, 0.2 + (m - 1) * (0.6 / 153))
-        what = f"cube<3>({m}) sub-block of the scene ({len(xs)} p, same spacing, 128^3 grid)"
-    elif workload == "cfg3":
-        m = 64
-        xs = nm.cube(3, m, 0.05, 0.05 + (m - 1) * (62.5 / 256 / 125))
-        what = f"{m}^3 sub-block ({len(xs)} p, same spacing, 256^3 grid)"
-    else:
-        xs, what = x, "the full scene"
-    return xs, model, res, dim, what
+        xs = nm.cube(3, 128, 0.25, 0.5)
+        return xs, model, 256, dim, ("half-scale replica of cfg4: cube<3>(128,0.25,0.5) = 2097152 p on a 256^3 grid "
+                                     "(same material/dt, 8 particles per cell, 8.1 grid nodes per particle as cfg4's 8.05)")
+    return x, model, res, dim, "the full scene"
 
 
 def host_cpu():
@@ -161,19 +159,39 @@ def host_cpu():
     return {"model": model, "cores_total": os.cpu_count()}
 
 
-def cpu_reference_rate(workload: str, steps: int, warmup: int, budget_s: float = 20.0):
+def cpu_reference_rate(workload: str, steps: int, warmup: int):
     from oracle import cpu_oracle as co
     kind = "ref_fast" if co.available("ref_fast") else "port"
-    xs, model, res, dim, what = cpu_sample(workload, budget_s)
+    xs, model, res, dim, what = cpu_sample(workload)
     sim = co.CpuSim(xs, model, res, kind=kind)
     if warmup:
         sim.time_advance(warmup)
     t = sim.time_advance(steps)
     rate = len(xs) * steps / t
     return dict(value=rate, unit="particle-steps/s", cores=1, kind="reference" if kind == "ref_fast" else "port",
-                host=host_cpu(),
-                sample=f"{what}; {steps} advance() steps in {t:.2f} s on 1 host core "
-                       f"({'reference nclr.h, -Ofast, Eigen stand-in' if kind == 'ref_fast' else 'oracle port, -O2'})"), t
+                host=host_cpu(), sample_particles=int(len(xs)), sample_grid_res=int(res),
+                sample=f"{what}; {steps} advance() steps (after {warmup} warm-up) in {t:.2f} s on 1 host core "
+                       f"({'reference nclr.h, -Ofast, Eigen stand-in' if kind == 'ref_fast' else 'oracle port, -O2'}; "
+                       "the reference is single-threaded: its omp pragmas are inert, CMakeLists.txt:9-10)"), t
+
+
+def cpu_full_scene(workload: str, steps: int = 2):
+    """Real full-scene reference steps (cfg4: ~4 GB of host memory, tens of seconds per step)."""
+    from oracle import cpu_oracle as co
+    kind = "ref_fast" if co.available("ref_fast") else "port"
+    x, model, res, desc = scene(workload)
+    sim = co.CpuSim(x, model, res, kind=kind)
+    per = [sim.time_advance(1) for _ in range(steps)]
+    return {"steps": steps, "seconds_per_step": per, "value": len(x) * steps / sum(per), "unit": "particle-steps/s",
+            "what": f"{desc}: the first {steps} advance() steps of the FULL scene on 1 host core"}
+
+
+def bench_config(args, desc, n_total, res, dim, model):
+    """`config` of the JSON line — the same dict for the GPU arm and for `--impl reference` (same workload)."""
+    return {"workload": desc, "particles": int(n_total), "grid_res": int(res), "dim": int(dim),
+            "material": ["snow", "jelly", "liquid"][model],
+            "l2_policy": "inputs larger than L2 (particle store + grid >> 126 MB)" if n_total * 116 > 2e8
+            else "working set smaller than L2 (scene is small); no flush"}
 
 
 def run_reference_arm(args):
@@ -181,18 +199,18 @@ def run_reference_arm(args):
     if rank != 0:
         return
     x, model, res, desc = scene(args.workload)
-    per_step_budget = max(1.0, 150.0 / max(1, args.steps + args.warmup))
-    cb, t = cpu_reference_rate(args.workload, args.steps, args.warmup, budget_s=per_step_budget)
+    cb, t = cpu_reference_rate(args.workload, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "particle-steps/s", "value": cb["value"], "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "particles": int(len(x)), "grid_res": res, "dim": int(x.shape[1]),
-                   "material": ["snow", "jelly", "liquid"][model]},
+        "config": bench_config(args, desc, len(x), res, x.shape[1], model),
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if cb["sample_particles"] != len(x) and args.gpus == 1 and not args.no_full_check:
+        line["full_scene"] = cpu_full_scene(args.workload, 2)   # cross-check of the replica's rate on the real scene
     print(json.dumps(line))
 
 
@@ -245,9 +263,17 @@ def run_gpu(args):
     sim.advance(prime)
     sim.advance(args.warmup)
     sync()
-    l0 = sim.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    peak, peak_src = measured_peak_gbs()
+    ab = ALGO_BYTES[dim]
+    steps_done = prime + args.warmup
+
+    def timed_window(clk_device=None):
+        """K steps between CUDA events on the sim's stream, then a separate per-phase pass (events per phase
+        serialise the step, so it is not part of the timed region)."""
+        nonlocal steps_done
+        first = steps_done
+        l0 = sim.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync()
         with torch.cuda.stream(stream):
             e0.record(stream)
@@ -255,33 +281,42 @@ def run_gpu(args):
             e1.record(stream)
         sync()
         ms = e0.elapsed_time(e1)
-    launches = sim.launch_count() - l0
-    clocks = clk.summary()
-    value = n_total * args.steps / (ms * 1e-3)
+        launches = sim.launch_count() - l0
+        sim.timing_enable(True)
+        sim.timing_read(reset=True)
+        prof_steps = min(args.steps, 20)
+        sim.advance(prof_steps)
+        sync()
+        tm = sim.timing_read(reset=True)
+        sim.timing_enable(False)
+        steps_done += args.steps + prof_steps
+        phases = {k + "_ms": tm[k] / max(1, tm["steps"]) for k in ("sort", "p2g", "grid", "g2p")}
+        kern = {k: {"ms": phases[k + "_ms"],
+                    "achieved_GBps": ab[k] * n_total / (phases[k + "_ms"] * 1e-3) / 1e9 if phases[k + "_ms"] > 0 else 0.0}
+                for k in ("p2g", "g2p")}
+        for k in kern:
+            kern[k]["frac"] = kern[k]["achieved_GBps"] / peak
+        return {"steps": [first, first + args.steps], "value": n_total * args.steps / (ms * 1e-3),
+                "ms_per_step": ms / args.steps, "phase_ms": phases, "kernels": kern, "launches": int(launches)}
 
-    # ---- per-phase timing (separate pass; events per phase serialise the step) ----------------
-    sim.timing_enable(True)
-    sim.timing_read(reset=True)
-    prof_steps = min(args.steps, 20)
-    sim.advance(prof_steps)
-    sync()
-    tm = sim.timing_read(reset=True)
-    sim.timing_enable(False)
-    peak, peak_src = measured_peak_gbs()
-    ab = ALGO_BYTES[dim]
-    phases = {}
-    for k in ("sort", "p2g", "grid", "g2p"):
-        phases[k + "_ms"] = tm[k] / max(1, tm["steps"])
+    with ClockSampler(local) as clk:
+        early = timed_window()
+    clocks = clk.summary()
+    value, ms, launches = early["value"], early["ms_per_step"] * args.steps, early["launches"]
+    phases = early["phase_ms"]
     dom = "g2p" if phases["g2p_ms"] >= phases["p2g_ms"] else "p2g"
-    dom_ms = phases[dom + "_ms"]
-    achieved = ab[dom] * n_total / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    achieved = early["kernels"][dom]["achieved_GBps"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": ncu_traffic(dom, n_total) if dim == 3 else None, "peak_source": peak_src,
-                "algorithmic_bytes_per_particle": ab[dom],
-                "other": {k: {"ms": phases[k + "_ms"],
-                              "achieved_GBps": ab[k] * n_total / (phases[k + "_ms"] * 1e-3) / 1e9 if phases[k + "_ms"] > 0 else 0.0}
-                          for k in ("p2g", "g2p")},
-                "phase_ms": phases}
+                "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
+                "traffic": ncu_traffic(dom, n_total) if dim == 3 else None, "peak_source": peak_src,
+                "algorithmic_bytes_per_particle": ab[dom], "other": early["kernels"], "phase_ms": phases}
+
+    # ---- late phase (under Q1 the snow turns into a particle gas that fills the box) ----
+    late = None
+    if args.late_step > steps_done:
+        sim.advance(args.late_step - steps_done)
+        steps_done = args.late_step
+        late = timed_window()
 
     # ---- end to end through the C-ABI with host buffers ---------------------------------------
     st = sim.particles()
@@ -317,18 +352,17 @@ def run_gpu(args):
     if args.no_cpu:
         cpu = None
     else:
-        cpu, _ = cpu_reference_rate(args.workload, 6 if n_total > 1_000_000 else 20, 0, budget_s=10.0)
+        cpu, _ = cpu_reference_rate(args.workload, 6 if n_total > 1_000_000 else 20, 0)
 
     line = {
         "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "particles": int(n_total), "grid_res": res, "dim": dim,
-                   "material": ["snow", "jelly", "liquid"][model], "sort_every": args.sort_every,
-                   "graph_priming_steps": prime,
-                   "l2_policy": "inputs larger than L2 (particle store + grid >> 126 MB)" if n_total * 116 > 2e8
-                   else "working set smaller than L2 (scene is small); no flush"},
+        "config": bench_config(args, desc, n_total, res, dim, model),
+        "run": {"sort_every": args.sort_every, "graph_priming_steps": prime, "p2g_variant": args.p2g_variant,
+                "timed_steps": early["steps"]},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "phases": {"early": early, "late": late},
     }
     print(json.dumps(line))
 
@@ -343,9 +377,15 @@ def main():
     ap.add_argument("--sort-every", type=int, default=4)
     ap.add_argument("--p2g-variant", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-full-check", action="store_true", help="--impl reference: skip the 2 real full-scene steps")
+    ap.add_argument("--late-step", type=int, default=-1,
+                    help="also time K steps starting at this step (late, dispersed phase); -1 = 300 for the 3D snow "
+                         "scenes, off otherwise; 0 = off")
     ap.add_argument("--rebalance-every", type=int, default=50, help="multi-GPU: re-balance slab boundaries every k steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
+    if args.late_step < 0:
+        args.late_step = 300 if args.workload in ("cfg4", "snow128") else 0
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -102,7 +102,10 @@ int nmpm_download_grid(nmpm_handle h, float *gv, float *gm, size_t *cells_out);
 int nmpm_download_grid_aos(nmpm_handle h, void *cells_aos, size_t stride, size_t *cells_out);
 
 /* Replace the particle state (teacher-forced parity tests / resume from a snapshot: the reference
- * does this by constructing a new sim from a saved particle vector).  n must match. */
+ * does this by constructing a new sim from a saved particle vector).  n must match.
+ * A NULL v / F / C / Jp means "the constructor default" (v = 0, F = diag<dim>(1), C = 0, Jp = 1,
+ * src/nclr.h:46-47), NOT "keep the device value"; mass and volume are always kept.  Allowed between steps
+ * and in the middle of a step (after nmpm_phase): the aborted step's grid sums are discarded. */
 int nmpm_upload_particles(nmpm_handle h, const float *x, const float *v, const float *F, const float *C,
                           const float *Jp);
 

@@ -36,7 +36,8 @@ def stale() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "nmpm.h"]
+    deps = (list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inl")) +
+            [PKG.parent / "include" / "nmpm.h"])
     return any(p.stat().st_mtime > t for p in deps)
 
 

@@ -250,8 +250,8 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
     fill_params(h, dt, E, nu, gravity);
     const size_t n1 = (size_t) res + 1;
     h->cells = (dim == 3) ? n1 * n1 * n1 : n1 * n1;
-    if (h->cells >= 0xFFFFFFFFull) {
-        g_create_error = "grid too large: (res+1)^dim must fit 32 bits";
+    if (h->cells >= 0x7FFFFFFFull) {  // node indices travel as 32-bit signed ints in the P2G packets
+        g_create_error = "grid too large: (res+1)^dim must be below 2^31";
         delete h;
         return NMPM_ERR_INVALID;
     }
@@ -884,6 +884,14 @@ int nmpm_upload_particles(nmpm_handle h, const float* x, const float* v, const f
     CUDA_TRY(h, e);
     ParticleStore& S = h->store[h->cur];
     ParticleStore& T = h->store[h->cur ^ 1];
+    if (h->phase_next != 0) {
+        // Upload in the middle of a step (after nmpm_phase(P2G) or (GRID_OP)): the aborted step's P2G has already
+        // written the nodes of box[box_cur], and the next step only clears box[box_cur-1] (which that P2G cleared
+        // itself) before the key pass rebuilds box[box_cur].  Zero those nodes now, or later steps would accumulate on
+        // top of the stale sums.
+        NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + h->box_cur, h->P.n1)));
+        h->launches++;
+    }
     // slots go back to input order: carry mass/volume over through id
     NMPM_DISPATCH_DIM(h, (k_restore_constants<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(S, T, (uint32_t) n)));
     NMPM_DISPATCH_DIM(h, (k_import_soa<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(dx, dv, dF, dC, dJ, nullptr,
@@ -897,9 +905,11 @@ int nmpm_upload_particles(nmpm_handle h, const float* x, const float* v, const f
     // the sort cadence restarts so that the next step re-bins the new state
     h->steps_done = 0;
     CUDA_TRY(h, cudaMemsetAsync(h->d_error, 0, sizeof(int), h->stream));
+    // the host copy of the flag is reset only after the stream has drained: an error-flag copy of an earlier
+    // nmpm_advance may still be in flight and would otherwise re-raise the old state's error for the new one
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     *h->h_error = 0;
     h->error_latched = false;
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return NMPM_OK;
 }
 

@@ -548,8 +548,8 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
         float2 mv = make_float2(0.0f, 0.0f);
         uint32_t pid = 0;
         if (perm || mig.left || moved) {
-            mv = __ldg(S.mv + src);
-            pid = __ldg(S.id + src);
+            mv = S.mv[src];   // coherent loads: the re-grouping below rewrites these arrays in place
+            pid = S.id[src];
         }
         if (moved) {
             const int lane = threadIdx.x & 31;

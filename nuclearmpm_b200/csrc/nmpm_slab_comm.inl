@@ -7,7 +7,16 @@
 // already has loaded (torch's), or from an explicit path.
 #include <cstdlib>
 #include <dlfcn.h>
+#if __has_include(<nccl.h>)
 #include <nccl.h>
+#else
+// NCCL is only ever reached through dlopen at run time; without its development header the handful of types
+// the entry points below use are declared here (ABI of NCCL 2.x), so the single-GPU library still builds.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclInt32 = 2, ncclFloat32 = 7 } ncclDataType_t;
+#endif
 
 namespace {
 

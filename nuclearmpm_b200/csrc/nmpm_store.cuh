@@ -76,12 +76,14 @@ __device__ __forceinline__ void load_for_p2g<2>(const ParticleStore& S, size_t i
     p.Jp = jp, p.mass = mv.x, p.volume = mv.y;
 }
 
-// G2P needs x, F, Jp only (v and C are overwritten: src/nclr.h:185-186)
+// G2P needs x, F, Jp only (v and C are overwritten: src/nclr.h:185-186).  Plain (coherent) loads, not
+// ld.global.nc: the in-place G2P writes other lanes' slots of these same arrays later in the kernel.
+__device__ __forceinline__ float4 ld4(const float4* p) { return *p; }
 template <int D>
 __device__ __forceinline__ void load_for_g2p(const ParticleStore& S, size_t i, PState<D>& p);
 template <>
 __device__ __forceinline__ void load_for_g2p<3>(const ParticleStore& S, size_t i, PState<3>& p) {
-    const float4 a0 = ldg4(S.q[0] + i), a1 = ldg4(S.q[1] + i), a2 = ldg4(S.q[2] + i), a3 = ldg4(S.q[3] + i);
+    const float4 a0 = ld4(S.q[0] + i), a1 = ld4(S.q[1] + i), a2 = ld4(S.q[2] + i), a3 = ld4(S.q[3] + i);
     p.x[0] = a0.x, p.x[1] = a0.y, p.x[2] = a0.z, p.Jp = a0.w;
     p.F.m[0] = a1.x, p.F.m[1] = a1.y, p.F.m[2] = a1.z, p.F.m[3] = a1.w;
     p.F.m[4] = a2.x, p.F.m[5] = a2.y, p.F.m[6] = a2.z, p.F.m[7] = a2.w;
@@ -89,10 +91,10 @@ __device__ __forceinline__ void load_for_g2p<3>(const ParticleStore& S, size_t i
 }
 template <>
 __device__ __forceinline__ void load_for_g2p<2>(const ParticleStore& S, size_t i, PState<2>& p) {
-    const float4 a0 = ldg4(S.q[0] + i), a1 = ldg4(S.q[1] + i);
+    const float4 a0 = ld4(S.q[0] + i), a1 = ld4(S.q[1] + i);
     p.x[0] = a0.x, p.x[1] = a0.y;
     p.F.m[0] = a1.x, p.F.m[1] = a1.y, p.F.m[2] = a1.z, p.F.m[3] = a1.w;
-    p.Jp = __ldg(S.s + i);
+    p.Jp = S.s[i];
 }
 
 // ---- stores (x, v, F, C, Jp; mass/volume/id are never rewritten by the step) ---------------

@@ -23,6 +23,13 @@ int run(int model, int res, int cube_res, float lo, float hi, int steps, const c
     f.write(reinterpret_cast<const char *>(ps.data()), std::streamsize(ps.size() * sizeof(nclr::Particle<dim>)));
     f.write(reinterpret_cast<const char *>(cells.data()), std::streamsize(cells.size() * sizeof(nclr::Cell<dim>)));
     std::printf("mu_0 %.9g lambda_0 %.9g colour %d\n", sim.mu_0, sim.lambda_0, ps.empty() ? 0 : ps[0].c);
+    // positions(): the frame hand-off of src/example.cpp:56-82 — same values and order as particles()[i].x
+    const auto &pos = sim.positions();
+    if (pos.size() != ps.size()) return 5;
+    for (std::size_t i = 0; i < ps.size(); ++i)
+        for (int d = 0; d < dim; ++d)
+            if (pos[i](d) != ps[i].x(d)) return 5;
+    std::printf("positions ok\n");
     // out-of-grid particle => std::out_of_range, like vector::at in the reference (src/nclr.h:163)
     std::vector<nclr::Particle<dim>> bad = {nclr::Particle<dim>(nclr::constvec<dim>(0.999f), 0)};
     nclr::MPMSimulation<dim> sim2(bad, nclr::MaterialModel::kJelly, res);

@@ -21,7 +21,7 @@ def test_cpp_caller_matches_oracle(tmp_path, dim, model, res, cres, steps):
     r = subprocess.run([str(exe), str(dim), str(model), str(res), str(cres), "0.4", "0.6", str(steps), str(out)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr + r.stdout
-    assert "out_of_range ok" in r.stdout
+    assert "out_of_range ok" in r.stdout and "positions ok" in r.stdout
     raw = out.read_bytes()
     n, psize, cells, csize = struct.unpack("4Q", raw[:32])
     assert psize == (64 if dim == 2 else 112) and csize == 4 * (dim + 1)

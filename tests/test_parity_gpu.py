@@ -405,3 +405,46 @@ def test_device_fast_polar_and_snow_projection(name):
     if well.any():
         assert np.abs(R - Ro)[well].max() <= TOL[name]
         assert np.abs(G - Go)[well].max() <= TOL[name]
+
+
+# ------------------------------------------------------------------------------------------
+def test_positions_only_download_matches_particles():
+    """N4: the positions-only hand-off a frame loop uses (src/example.cpp:56-82 reads just p.x every 10th step):
+    nmpm_download_positions == the x of nmpm_download_particles, in input order, on re-binned and in-place steps."""
+    rng = np.random.default_rng(41)
+    for dim, model in [(2, co.SNOW), (3, co.JELLY)]:
+        x = rng.uniform(0.3, 0.7, (3000, dim)).astype(np.float32)
+        rng.shuffle(x, axis=0)
+        gpu = nm.MPMSimulation(x, model, 64 if dim == 2 else 32)
+        cpu = co.CpuSim(x, model, 64 if dim == 2 else 32)
+        assert (gpu.positions() == x).all()          # before the first step: the input, in input order
+        for step in range(6):                        # sort cadence 4: steps 0 and 4 re-bin, the others run in place
+            gpu.advance(1)
+            cpu.advance(1)
+            pos = gpu.positions()
+            assert pos.shape == (3000, dim) and (pos == gpu.particles()["x"]).all()
+            assert np.abs(pos - cpu.particles()["x"]).max() <= TOL_X * (step + 1)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("after_phase", [0, 1])
+def test_upload_in_the_middle_of_a_step_discards_the_partial_grid(dim, after_phase):
+    """nmpm_upload_particles after nmpm_phase(P2G) / (GRID_OP): the aborted step's node sums must not leak into the
+    following steps (the next step clears only the box of the previous COMPLETE P2G)."""
+    rng = np.random.default_rng(7 + dim)
+    n = 2000
+    res = 64 if dim == 2 else 32
+    xa = rng.uniform(0.55, 0.75, (n, dim)).astype(np.float32)   # the aborted step's particles: a different region
+    xb = rng.uniform(0.25, 0.45, (n, dim)).astype(np.float32)
+    v = rng.normal(0, 1, (n, dim)).astype(np.float32)
+    gpu = nm.MPMSimulation(xa, co.JELLY, res, v=v)
+    gpu.advance(1)
+    for ph in range(after_phase + 1):
+        gpu.phase(ph)
+    gpu.upload(xb, v)
+    cpu = co.CpuSim(xb, co.JELLY, res, v=v)
+    for step in range(3):
+        gpu.advance(1)
+        cpu.advance(1)
+        check_grid(*gpu.grid(), *cpu.grid(), f"grid after upload, step {step + 1}")
+        check_state(gpu.particles(), cpu.particles(), f"state after upload, step {step + 1}", scale=step + 1.0)
