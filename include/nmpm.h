@@ -58,7 +58,11 @@ typedef struct nmpm_options {
     int slab_x0;      /* multi-GPU x-slab: this sim owns particles with slab_x0 <= base.x < slab_x1 */
     int slab_x1;      /* 0 (default) = not a slab: the sim owns the whole domain */
     int capacity;     /* slab mode: particle slots to allocate (>= n; room for migrants). 0 = n */
-    int reserved[9];
+    int g2p_window;   /* 3D G2P node gather: 0 = auto, 1 = straight from global memory (L1/L2),
+                         2 = node window of each 128-particle CTA staged in shared memory by the TMA
+                         (cp.async.bulk.tensor + mbarrier; CTAs whose bounding box exceeds the window fall back to 1).
+                         Env NMPM_G2P_WINDOW=0/1 overrides.  Same results up to nothing: both read the same nodes */
+    int reserved[8];
 } nmpm_options;
 
 void nmpm_default_options(nmpm_options *opt);

@@ -10,6 +10,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "../../include/nmpm.h"
@@ -67,6 +68,8 @@ struct nmpm_sim {
     struct nmpm_slab_comm* sc = nullptr;            // native slab step (nmpm_slab_comm.inl)
     bool box_valid = false;   // box[box_cur] describes store[cur]
     bool local_reorder = true;  // in-place G2P re-groups each warp's 32 slots by cell key (NMPM_LOCAL_REORDER=0: off)
+    CUtensorMap grid_map{};     // 3D: the grid as a rank-4 tensor {4 floats, z, y, x} with one x-plane window box (G2P)
+    bool g2p_window = false;    // 3D: G2P stages its node window through the TMA (NMPM_G2P_WINDOW=0: off)
     bool p2g_early = false;   // slab mode: the in-place P2G of the coming step was issued before the migrants arrived
     bool grid_valid = false;  // false until the first p2g: the reference's grid() is empty (src/solver.cpp:52-57)
 
@@ -207,6 +210,30 @@ static void fill_params(nmpm_sim* h, float dt, float E, float nu, float gravity)
     P.dt_gravity = dt * gravity;
 }
 
+// The dense grid as a TMA tensor: rank 4 {4 floats of a node, z, y, x}, box = one x-plane of the G2P node window
+// (nmpm_kernels.cuh: kWinY x kWinZ nodes).  Out-of-range box parts (beyond node res) are filled with zeros.
+static int make_grid_map(nmpm_sim* h) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return NMPM_ERR_CUDA;
+    }
+    const cuuint64_t n1 = (cuuint64_t) h->res + 1;
+    const cuuint64_t dims[4] = {4, n1, n1, n1};
+    const cuuint64_t strides[3] = {16, 16 * n1, 16 * n1 * n1};  // bytes, dims 1..3
+    const cuuint32_t box[4] = {4, (cuuint32_t) kWinZ, (cuuint32_t) kWinY, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = reinterpret_cast<EncodeFn>(fn)(&h->grid_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, h->grid, dims, strides, box,
+                                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? NMPM_OK : NMPM_ERR_CUDA;
+}
+
 static int create_common(int dim, int model, int res, float dt, float E, float nu, float gravity, size_t n,
                          const nmpm_options* opt, nmpm_sim** out) {
     if (!out) return NMPM_ERR_INVALID;
@@ -276,6 +303,12 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
     if (int rc = alloc_store(h, h->store[1])) return rc;
     CUDA_TRY(h, cudaMalloc(&h->grid, h->cells * sizeof(float4)));
     CUDA_TRY(h, cudaMemset(h->grid, 0, h->cells * sizeof(float4)));  // the only dense clear; afterwards box by box
+    if (dim == 3) {
+        // auto = global gather: measured on cfg4, the staged window is 5 % slower (profiles/r02c)
+        bool want = h->opt.g2p_window == 2;
+        if (const char* gw = std::getenv("NMPM_G2P_WINDOW")) want = (*gw != '0');
+        h->g2p_window = want && make_grid_map(h) == NMPM_OK;  // no tensor map: plain global gather
+    }
     CUDA_TRY(h, cudaMalloc(&h->d_box, kBoxRing * sizeof(GridBox)));
     CUDA_TRY(h, cudaMalloc(&h->d_box_partial, ((h->cap + 127) / 128 * 4 + 4) * 8 * sizeof(int)));
     for (int k = 0; k < kBoxRing; ++k) k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + k);
@@ -586,9 +619,25 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
     const uint32_t* gone_keys = (h->slab && !h->perm && (h->n_gone || h->p2g_early)) ? h->sort.keys_a : nullptr;
     const int box_next = (h->box_cur + 1) % kBoxRing;
     k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + box_next);
-    NMPM_DISPATCH(h, (k_g2p_gather<D, MODEL><<<blocks_for(n, 128), 128, 0, h->stream>>>(
-                         S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error, mig,
-                         h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0)));
+    if (h->g2p_window) {  // 3D only (set at creation)
+        constexpr int D = 3;
+        if (h->model == 0)
+            k_g2p_gather<D, 0, true><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out,
+                                                                               h->tiles_per_axis, h->d_error, mig, h->d_box_partial,
+                                                                               gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
+        else if (h->model == 1)
+            k_g2p_gather<D, 1, true><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out,
+                                                                               h->tiles_per_axis, h->d_error, mig, h->d_box_partial,
+                                                                               gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
+        else
+            k_g2p_gather<D, 2, true><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out,
+                                                                               h->tiles_per_axis, h->d_error, mig, h->d_box_partial,
+                                                                               gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
+    } else {
+        NMPM_DISPATCH(h, (k_g2p_gather<D, MODEL, false><<<blocks_for(n, 128), 128, 0, h->stream>>>(
+                             S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error, mig,
+                             h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map)));
+    }
     {   // warps of the launch above (128-thread CTAs): every one of them wrote a partial box
         const uint32_t nwarps = blocks_for(n, 128) * 4u - ((blocks_for(n, 128) * 128u - n) / 32u);
         const unsigned rb = nwarps / 1024 + 1 < 148u ? nwarps / 1024 + 1 : 148u;

@@ -2,6 +2,7 @@
 // Reference semantics: src/nclr.h:104-165 (p2g), :263-310 (grid_op), :167-261 (g2p).
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "nmpm_math.cuh"
@@ -391,135 +392,129 @@ __device__ __forceinline__ void g2p_update(PState<D>& p, const Mat<D>& Cn, const
     }
 }
 
-// `perm` (nullable) fuses the re-binning reorder into this kernel: thread i reads slot perm[i] of `S`
-// and writes slot i of `T` (T may equal S when perm is null), so after the kernel `T` is in cell-sorted
-// order without a separate gather pass.  `keys_out` (nullable) receives the NEXT step's cell key of
-// the advected particle, so the next step's sort starts without a key pass.
-template <int D, int MODEL>
-__global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore S, ParticleStore T, const uint32_t* __restrict__ perm,
-                                                    uint32_t n, MaterialParams P, const float4* __restrict__ grid,
-                                                    uint32_t* __restrict__ keys_out, int tiles_per_axis,
-                                                    int* __restrict__ error_flag, MigrateArgs mig,
-                                                    int* __restrict__ box_partial, const uint32_t* __restrict__ gone_keys,
-                                                    int local_reorder) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    // slab mode between sorts: a slot whose particle migrated away is skipped (its key stays kKeyGone)
-    const bool mine = i < n && !(gone_keys && __ldg(gone_keys + i) == kKeyGone);
-    const unsigned live = __ballot_sync(0xffffffffu, mine);
-    if (live == 0u) {  // nobody here owns a particle: leave an empty partial box (k_box_reduce reads every warp's slot)
-        if ((threadIdx.x & 31) == 0) {
-            int4* out = reinterpret_cast<int4*>(box_partial + (size_t) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8);
-            out[0] = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, (int) 0x80000000);
-            out[1] = make_int4((int) 0x80000000, (int) 0x80000000, 0, 0);
-        }
-        return;
-    }
-    if (!mine) return;
-    const uint32_t src = perm ? __ldg(perm + i) : i;
-    PState<D> p;
-    load_for_g2p<D>(S, src, p);
-    const bool reorder = local_reorder && !mig.left && !gone_keys;  // warp-uniform (kernel arguments); single GPU only
-    int base[D];
-    float fx[D], w[D][3];
-    if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
-    // Gather with the stencil offsets centred on the middle node:  o = ijk - 1 in {-1,0,+1},
-    //   v   = sum w g
-    //   B_c = sum w g o_c                  (the o_c = 0 terms vanish at compile time)
-    //   C   = 4 inv_dx (B - v (fx-1)^T)    == sum 4 inv_dx (w g) (ijk - fx)^T   (src/nclr.h:206,223)
-    const int n1 = P.n1;
-    const float four_inv_dx = 4.0f * P.inv_dx;
-    float vn[D];
-    Mat<D> Cn;
-    if constexpr (D == 3) {
-        // Sum factorisation: w = wx_i wy_j wz_k is separable, so the 27-node sums are three nested 3-term
-        // sums — along z per (i,j) row (three adjacent float4 nodes), along y per i, along x — and the weight
-        // products are never formed: 126 packed instructions instead of ~270.  Packed pairs: (x,y) components,
-        // and (plain, z-offset-weighted) sums of the z component, which share their operands.
-        const float4* gp = grid + ((size_t) (base[0] * n1 + base[1]) * n1 + base[2]);
-        const int plane = n1 * n1;
-        const float2 wz0 = splat2g(w[2][0]), wz1 = splat2g(w[2][1]), wz2 = splat2g(w[2][2]), nwz0 = splat2g(-w[2][0]);
-        const float2 wzp0 = make_float2(w[2][0], -w[2][0]), wzp1 = make_float2(w[2][1], 0.0f), wzp2 = wz2;
-        float2 v01, vzBzz, Bz01, By01, Bx01;  // v.xy | (v.z, B_z.z) | B_z.xy | B_y.xy | B_x.xy
-        float Byz, Bxz;
+// ---- async copy plumbing (sm_90+ PTX): mbarrier + TMA tensor loads into shared memory --------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0u;
+}
+// one box of a rank-4 tensor map (coordinates fastest axis first) -> shared memory, completion on `bar`
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// Node window of the TMA-staged G2P: up to kWinX x-planes of kWinY x kWinZ nodes (float4), one TMA box per plane
+// (tensor-map box {4 floats, kWinZ, kWinY, 1}); planes sit kWinPitch nodes apart (128-byte aligned for the TMA).
+// kWinZ = 13 (odd): rows of a plane start 13 nodes apart, which spreads the 16-byte bank groups of neighbouring rows.
+constexpr int kWinX = 8, kWinY = 12, kWinZ = 13;
+constexpr int kWinPitch = 160;                           // >= kWinY * kWinZ = 156, multiple of 8 nodes (128 B)
+constexpr uint32_t kWinPlaneBytes = kWinY * kWinZ * 16;  // bytes one TMA box delivers
+
+// ---- K4 helpers --------------------------------------------------------------------------------
+// Where the 27 stencil nodes of a particle come from: the dense grid in global memory (three adjacent float4
+// nodes per (i,j) row), or a node window staged in shared memory by the TMA (nmpm_g2p_tile.cuh) whose strides
+// are compile-time constants, so that all 27 loads are one base register plus an immediate offset.
+struct GlobalNodes {
+    const float4* gp;  // node (base.x, base.y, base.z)
+    int plane, n1;
+    __device__ __forceinline__ float4 load(int ii, int jj, int kk) const { return __ldg(gp + (ii * plane + jj * n1) + kk); }
+};
+template <int PLANE, int ROW>
+struct WindowNodes {
+    const float4* sp;  // node (base - window origin) of the shared-memory window
+    __device__ __forceinline__ float4 load(int ii, int jj, int kk) const { return sp[ii * PLANE + jj * ROW + kk]; }
+};
+
+// Gather with the stencil offsets centred on the middle node:  o = ijk - 1 in {-1,0,+1},
+//   v   = sum w g
+//   B_c = sum w g o_c                  (the o_c = 0 terms vanish at compile time)
+//   C   = 4 inv_dx (B - v (fx-1)^T)    == sum 4 inv_dx (w g) (ijk - fx)^T   (src/nclr.h:206,223)
+// Sum factorisation: w = wx_i wy_j wz_k is separable, so the 27-node sums are three nested 3-term sums — along z
+// per (i,j) row, along y per i, along x — and the weight products are never formed: 126 packed instructions
+// instead of ~270.  Packed pairs: (x,y) components, and (plain, z-offset-weighted) sums of the z component.
+template <class Nodes>
+__device__ __forceinline__ void g2p_gather3(const Nodes& nodes, const float (&w)[3][3], const float (&fx)[3],
+                                            float four_inv_dx, float (&vn)[3], Mat<3>& Cn) {
+    const float2 wz0 = splat2g(w[2][0]), wz1 = splat2g(w[2][1]), wz2 = splat2g(w[2][2]), nwz0 = splat2g(-w[2][0]);
+    const float2 wzp0 = make_float2(w[2][0], -w[2][0]), wzp1 = make_float2(w[2][1], 0.0f), wzp2 = wz2;
+    float2 v01, vzBzz, Bz01, By01, Bx01;  // v.xy | (v.z, B_z.z) | B_z.xy | B_y.xy | B_x.xy
+    float Byz, Bxz;
 #pragma unroll
-        for (int ii = 0; ii < 3; ++ii) {
-            float2 t01, tzz, tz01, ty01;  // sums over (j,k) of this i: t.xy | (t.z, t_z.z) | t_z.xy | t_y.xy
-            float tyz;
+    for (int ii = 0; ii < 3; ++ii) {
+        float2 t01, tzz, tz01, ty01;  // sums over (j,k) of this i: t.xy | (t.z, t_z.z) | t_z.xy | t_y.xy
+        float tyz;
 #pragma unroll
-            for (int jj = 0; jj < 3; ++jj) {
-                const float4* row = gp + (ii * plane + jj * n1);  // 32-bit offset: < 3 * 513^2
-                const float4 g0 = ldg4(row), g1 = ldg4(row + 1), g2 = ldg4(row + 2);
-                float2 s01 = __fmul2_rn(wz0, make_float2(g0.x, g0.y));
-                s01 = __ffma2_rn(wz1, make_float2(g1.x, g1.y), s01);
-                s01 = __ffma2_rn(wz2, make_float2(g2.x, g2.y), s01);
-                float2 sz01 = __fmul2_rn(wz2, make_float2(g2.x, g2.y));
-                sz01 = __ffma2_rn(nwz0, make_float2(g0.x, g0.y), sz01);
-                float2 szz = __fmul2_rn(wzp0, splat2g(g0.z));  // (sum wz g.z, sum wz o_z g.z)
-                szz = __ffma2_rn(wzp1, splat2g(g1.z), szz);
-                szz = __ffma2_rn(wzp2, splat2g(g2.z), szz);
-                const float2 wy = splat2g(w[1][jj]);
-                if (jj == 0) {
-                    t01 = __fmul2_rn(wy, s01), tzz = __fmul2_rn(wy, szz), tz01 = __fmul2_rn(wy, sz01);
-                    ty01 = __fmul2_rn(splat2g(-w[1][0]), s01);
-                    tyz = -w[1][0] * szz.x;
-                } else {
-                    t01 = __ffma2_rn(wy, s01, t01), tzz = __ffma2_rn(wy, szz, tzz), tz01 = __ffma2_rn(wy, sz01, tz01);
-                    if (jj == 2) {
-                        ty01 = __ffma2_rn(wy, s01, ty01);
-                        tyz = fmaf(w[1][2], szz.x, tyz);
-                    }
-                }
-            }
-            const float2 wx = splat2g(w[0][ii]);
-            if (ii == 0) {
-                v01 = __fmul2_rn(wx, t01), vzBzz = __fmul2_rn(wx, tzz), Bz01 = __fmul2_rn(wx, tz01);
-                By01 = __fmul2_rn(wx, ty01), Byz = w[0][0] * tyz;
-                Bx01 = __fmul2_rn(splat2g(-w[0][0]), t01), Bxz = -w[0][0] * tzz.x;
+        for (int jj = 0; jj < 3; ++jj) {
+            const float4 g0 = nodes.load(ii, jj, 0), g1 = nodes.load(ii, jj, 1), g2 = nodes.load(ii, jj, 2);
+            float2 s01 = __fmul2_rn(wz0, make_float2(g0.x, g0.y));
+            s01 = __ffma2_rn(wz1, make_float2(g1.x, g1.y), s01);
+            s01 = __ffma2_rn(wz2, make_float2(g2.x, g2.y), s01);
+            float2 sz01 = __fmul2_rn(wz2, make_float2(g2.x, g2.y));
+            sz01 = __ffma2_rn(nwz0, make_float2(g0.x, g0.y), sz01);
+            float2 szz = __fmul2_rn(wzp0, splat2g(g0.z));  // (sum wz g.z, sum wz o_z g.z)
+            szz = __ffma2_rn(wzp1, splat2g(g1.z), szz);
+            szz = __ffma2_rn(wzp2, splat2g(g2.z), szz);
+            const float2 wy = splat2g(w[1][jj]);
+            if (jj == 0) {
+                t01 = __fmul2_rn(wy, s01), tzz = __fmul2_rn(wy, szz), tz01 = __fmul2_rn(wy, sz01);
+                ty01 = __fmul2_rn(splat2g(-w[1][0]), s01);
+                tyz = -w[1][0] * szz.x;
             } else {
-                v01 = __ffma2_rn(wx, t01, v01), vzBzz = __ffma2_rn(wx, tzz, vzBzz), Bz01 = __ffma2_rn(wx, tz01, Bz01);
-                By01 = __ffma2_rn(wx, ty01, By01), Byz = fmaf(w[0][ii], tyz, Byz);
-                if (ii == 2) Bx01 = __ffma2_rn(wx, t01, Bx01), Bxz = fmaf(w[0][2], tzz.x, Bxz);
-            }
-        }
-        vn[0] = v01.x, vn[1] = v01.y, vn[2] = vzBzz.x;
-        const float Bc[3][3] = {{Bx01.x, Bx01.y, Bxz}, {By01.x, By01.y, Byz}, {Bz01.x, Bz01.y, vzBzz.y}};  // Bc[c][r]
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float fc = fx[c] - 1.0f;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) Cn(r, c) = four_inv_dx * fmaf(-vn[r], fc, Bc[c][r]);
-        }
-    } else {
-        float2 v01 = make_float2(0.0f, 0.0f), B01[D];
-#pragma unroll
-        for (int c = 0; c < D; ++c) B01[c] = make_float2(0.0f, 0.0f);
-        const float2 plus1 = make_float2(1.0f, 1.0f), minus1 = make_float2(-1.0f, -1.0f);
-#pragma unroll
-        for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-            for (int jj = 0; jj < 3; ++jj) {
-                const size_t node = (size_t) (base[0] + ii) * n1 + (base[1] + jj);
-                const float4 g = ldg4(grid + node);
-                const float weight = w[0][ii] * w[1][jj];
-                const float2 wv01 = __fmul2_rn(make_float2(weight, weight), make_float2(g.x, g.y));
-                v01 = __fadd2_rn(v01, wv01);
-                const int o[2] = {ii - 1, jj - 1};
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (o[c] == 1) B01[c] = __ffma2_rn(wv01, plus1, B01[c]);
-                    else if (o[c] == -1)
-                        B01[c] = __ffma2_rn(wv01, minus1, B01[c]);
+                t01 = __ffma2_rn(wy, s01, t01), tzz = __ffma2_rn(wy, szz, tzz), tz01 = __ffma2_rn(wy, sz01, tz01);
+                if (jj == 2) {
+                    ty01 = __ffma2_rn(wy, s01, ty01);
+                    tyz = fmaf(w[1][2], szz.x, tyz);
                 }
             }
-        vn[0] = v01.x, vn[1] = v01.y;
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-            const float fc = fx[c] - 1.0f;
-            Cn(0, c) = four_inv_dx * fmaf(-vn[0], fc, B01[c].x);
-            Cn(1, c) = four_inv_dx * fmaf(-vn[1], fc, B01[c].y);
+        }
+        const float2 wx = splat2g(w[0][ii]);
+        if (ii == 0) {
+            v01 = __fmul2_rn(wx, t01), vzBzz = __fmul2_rn(wx, tzz), Bz01 = __fmul2_rn(wx, tz01);
+            By01 = __fmul2_rn(wx, ty01), Byz = w[0][0] * tyz;
+            Bx01 = __fmul2_rn(splat2g(-w[0][0]), t01), Bxz = -w[0][0] * tzz.x;
+        } else {
+            v01 = __ffma2_rn(wx, t01, v01), vzBzz = __ffma2_rn(wx, tzz, vzBzz), Bz01 = __ffma2_rn(wx, tz01, Bz01);
+            By01 = __ffma2_rn(wx, ty01, By01), Byz = fmaf(w[0][ii], tyz, Byz);
+            if (ii == 2) Bx01 = __ffma2_rn(wx, t01, Bx01), Bxz = fmaf(w[0][2], tzz.x, Bxz);
         }
     }
+    vn[0] = v01.x, vn[1] = v01.y, vn[2] = vzBzz.x;
+    const float Bc[3][3] = {{Bx01.x, Bx01.y, Bxz}, {By01.x, By01.y, Byz}, {Bz01.x, Bz01.y, vzBzz.y}};  // Bc[c][r]
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float fc = fx[c] - 1.0f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) Cn(r, c) = four_inv_dx * fmaf(-vn[r], fc, Bc[c][r]);
+    }
+}
+
+// Everything after the gather: F/Jp/C update, the next step's cell key, the warp-local re-grouping, the stores,
+// slab migration and the warp's partial node box.
+template <int D, int MODEL>
+__device__ __forceinline__ void g2p_finish(PState<D>& p, const Mat<D>& Cn, const float (&vn)[D], const ParticleStore& S,
+                                           const ParticleStore& T, const uint32_t* __restrict__ perm, uint32_t src, uint32_t i,
+                                           unsigned live, const MaterialParams& P, uint32_t* __restrict__ keys_out,
+                                           int tiles_per_axis, const MigrateArgs& mig, int* __restrict__ box_partial,
+                                           const uint32_t* __restrict__ gone_keys, int local_reorder) {
     g2p_update<D, MODEL>(p, Cn, vn, P);
+    const bool reorder = local_reorder && !mig.left && !gone_keys;  // warp-uniform (kernel arguments); single GPU only
     {   // bin the advected particle for the NEXT step: cell key, slab owner, node box
         int b[D];
         bool bad = false;
@@ -595,6 +590,157 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
         // migrants stay in the sender's box: the box table of the slab protocol must cover them until they are unpacked
         box_partial_write<D>(box_partial, live, b, true);
     }
+}
+
+// `perm` (nullable) fuses the re-binning reorder into this kernel: thread i reads slot perm[i] of `S`
+// and writes slot i of `T` (T may equal S when perm is null), so after the kernel `T` is in cell-sorted
+// order without a separate gather pass.  `keys_out` (nullable) receives the NEXT step's cell key of
+// the advected particle, so the next step's sort starts without a key pass.
+//
+// WINDOW (3D): the grid nodes the CTA's 128 particles touch are staged in shared memory by the TMA.  Slots are
+// cell-sorted (and stay grouped between two sorts: a particle moves < 1 cell per step), so the stencil bases of a CTA
+// span a few cells per axis: the CTA reduces the bounding box of its bases, one thread issues one
+// cp.async.bulk.tensor box per x-plane of the node window onto an mbarrier, the F rows of the particles are loaded
+// while the boxes are in flight, and the 27-node gather reads shared memory (one base register + immediate offsets,
+// 29-cycle latency) instead of 27 dependent-latency L1/L2 loads.  A CTA whose box does not fit the window (sparse or
+// dispersed particles, a chunk that straddles the end of a tile row) gathers from global memory as before.
+template <int D, int MODEL, bool WINDOW = false>
+__global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore S, ParticleStore T, const uint32_t* __restrict__ perm,
+                                                    uint32_t n, MaterialParams P, const float4* __restrict__ grid,
+                                                    uint32_t* __restrict__ keys_out, int tiles_per_axis,
+                                                    int* __restrict__ error_flag, MigrateArgs mig,
+                                                    int* __restrict__ box_partial, const uint32_t* __restrict__ gone_keys,
+                                                    int local_reorder, const __grid_constant__ CUtensorMap grid_map) {
+    static_assert(!WINDOW || D == 3, "the TMA node window is a 3D path");
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // slab mode between sorts: a slot whose particle migrated away is skipped (its key stays kKeyGone)
+    const bool mine = i < n && !(gone_keys && __ldg(gone_keys + i) == kKeyGone);
+    const unsigned live = __ballot_sync(0xffffffffu, mine);
+    if (live == 0u) {  // nobody here owns a particle: leave an empty partial box (k_box_reduce reads every warp's slot)
+        if ((threadIdx.x & 31) == 0) {
+            int4* out = reinterpret_cast<int4*>(box_partial + (size_t) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8);
+            out[0] = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, (int) 0x80000000);
+            out[1] = make_int4((int) 0x80000000, (int) 0x80000000, 0, 0);
+        }
+        if constexpr (!WINDOW) return;
+    }
+    if constexpr (!WINDOW) {
+        if (!mine) return;
+    }
+    const uint32_t src = (mine && perm) ? __ldg(perm + i) : i;
+    PState<D> p;
+    int base[D];
+    float fx[D], w[D][3];
+    [[maybe_unused]] bool in_window = false;            // WINDOW: the CTA's node box fits the window and has landed
+    [[maybe_unused]] const float4* win_node = nullptr;  // WINDOW: this particle's base node inside the window
+    if constexpr (WINDOW) {
+        __shared__ __align__(128) float4 win[kWinX * kWinPitch];
+        __shared__ __align__(8) uint64_t mbar;
+        __shared__ int red[4][8];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (threadIdx.x == 0) mbar_init(&mbar, 1);
+        // positions first: the window origin depends on them
+        float4 a0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (mine) a0 = ld4(S.q[0] + src);
+        p.x[0] = a0.x, p.x[1] = a0.y, p.x[2] = a0.z, p.Jp = a0.w;
+        bool ok = stencil_of<D>(p.x, P, base, fx, w);
+        if (mine && !ok) atomicOr(error_flag, 1);
+        int mn[3], mx[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            mn[d] = __reduce_min_sync(0xffffffffu, mine ? base[d] : 0x7fffffff);
+            mx[d] = __reduce_max_sync(0xffffffffu, mine ? base[d] : (int) 0x80000000);
+        }
+        if (lane == 0) {
+            *reinterpret_cast<int4*>(&red[warp][0]) = make_int4(mn[0], mn[1], mn[2], mx[0]);
+            *reinterpret_cast<int2*>(&red[warp][4]) = make_int2(mx[1], mx[2]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int wi = 0; wi < 4; ++wi) {
+            const int4 a = *reinterpret_cast<const int4*>(&red[wi][0]);
+            const int2 b = *reinterpret_cast<const int2*>(&red[wi][4]);
+            mn[0] = min(mn[0], a.x), mn[1] = min(mn[1], a.y), mn[2] = min(mn[2], a.z);
+            mx[0] = max(mx[0], a.w), mx[1] = max(mx[1], b.x), mx[2] = max(mx[2], b.y);
+        }
+        // node extents: bases lo..hi, stencil reaches +2 (CTA-uniform; an empty CTA has hi < lo and fails the test)
+        const int ex = mx[0] - mn[0] + 3, ey = mx[1] - mn[1] + 3, ez = mx[2] - mn[2] + 3;
+        in_window = ex >= 3 && ey >= 3 && ez >= 3 && ex <= kWinX && ey <= kWinY && ez <= kWinZ;
+        if (in_window && threadIdx.x == 0) {
+            mbar_arrive_expect_tx(&mbar, (uint32_t) ex * kWinPlaneBytes);
+            for (int px = 0; px < ex; ++px) tma_load_4d(win + px * kWinPitch, &grid_map, &mbar, 0, mn[2], mn[1], mn[0] + px);
+        }
+        // the F rows travel while the boxes are in flight
+        if (mine) {
+            const float4 a1 = ld4(S.q[1] + src), a2 = ld4(S.q[2] + src), a3 = ld4(S.q[3] + src);
+            p.F.m[0] = a1.x, p.F.m[1] = a1.y, p.F.m[2] = a1.z, p.F.m[3] = a1.w;
+            p.F.m[4] = a2.x, p.F.m[5] = a2.y, p.F.m[6] = a2.z, p.F.m[7] = a2.w;
+            p.F.m[8] = a3.x;
+        }
+        if (in_window) {
+            // bounded wait: a box that never lands (it cannot, short of a bad descriptor) must not hang the device
+            uint32_t spins = 0;
+            while (!mbar_try_wait(&mbar, 0u)) {
+                if (++spins > (1u << 22)) {
+                    in_window = false;
+                    atomicOr(error_flag, 4);
+                    break;
+                }
+            }
+        }
+        if (!mine) return;
+        win_node = win + ((base[0] - mn[0]) * kWinPitch + (base[1] - mn[1]) * kWinZ + (base[2] - mn[2]));
+    } else {
+        load_for_g2p<D>(S, src, p);
+        if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
+    }
+    // Gather with the stencil offsets centred on the middle node:  o = ijk - 1 in {-1,0,+1},
+    //   v   = sum w g
+    //   B_c = sum w g o_c                  (the o_c = 0 terms vanish at compile time)
+    //   C   = 4 inv_dx (B - v (fx-1)^T)    == sum 4 inv_dx (w g) (ijk - fx)^T   (src/nclr.h:206,223)
+    const int n1 = P.n1;
+    const float four_inv_dx = 4.0f * P.inv_dx;
+    float vn[D];
+    Mat<D> Cn;
+    if constexpr (D == 3) {
+        if (WINDOW && in_window) {
+            g2p_gather3(WindowNodes<kWinPitch, kWinZ>{win_node}, w, fx, four_inv_dx, vn, Cn);
+        } else {
+            const GlobalNodes nodes{grid + ((size_t) (base[0] * n1 + base[1]) * n1 + base[2]), n1 * n1, n1};
+            g2p_gather3(nodes, w, fx, four_inv_dx, vn, Cn);
+        }
+    } else {
+        float2 v01 = make_float2(0.0f, 0.0f), B01[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) B01[c] = make_float2(0.0f, 0.0f);
+        const float2 plus1 = make_float2(1.0f, 1.0f), minus1 = make_float2(-1.0f, -1.0f);
+#pragma unroll
+        for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) {
+                const size_t node = (size_t) (base[0] + ii) * n1 + (base[1] + jj);
+                const float4 g = ldg4(grid + node);
+                const float weight = w[0][ii] * w[1][jj];
+                const float2 wv01 = __fmul2_rn(make_float2(weight, weight), make_float2(g.x, g.y));
+                v01 = __fadd2_rn(v01, wv01);
+                const int o[2] = {ii - 1, jj - 1};
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (o[c] == 1) B01[c] = __ffma2_rn(wv01, plus1, B01[c]);
+                    else if (o[c] == -1)
+                        B01[c] = __ffma2_rn(wv01, minus1, B01[c]);
+                }
+            }
+        vn[0] = v01.x, vn[1] = v01.y;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const float fc = fx[c] - 1.0f;
+            Cn(0, c) = four_inv_dx * fmaf(-vn[0], fc, B01[c].x);
+            Cn(1, c) = four_inv_dx * fmaf(-vn[1], fc, B01[c].y);
+        }
+    }
+    g2p_finish<D, MODEL>(p, Cn, vn, S, T, perm, src, i, live, P, keys_out, tiles_per_axis, mig, box_partial, gone_keys,
+                         local_reorder);
 }
 
 // slab migration, receiving side: append records to slots [first, first + count) and bin them

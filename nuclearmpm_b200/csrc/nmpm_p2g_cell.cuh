@@ -33,6 +33,10 @@ namespace nmpm {
 
 constexpr int kP2GWarps = 4;
 constexpr int kP2GColsMinB = 6;  // CTAs per SM of the column-lane kernels: 80 registers, no spills in the node walk
+#ifndef NMPM_P2G_STREAMS_MINB
+#define NMPM_P2G_STREAMS_MINB 5
+#endif
+constexpr int kP2GStreamsMinB = NMPM_P2G_STREAMS_MINB;
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
@@ -279,41 +283,45 @@ __global__ void __launch_bounds__(kP2GWarps * 32, kP2GColsMinB) k_p2g_cols(Parti
     const int s_begin = 11 * g;
     const int s_end = min((g == 2) ? 32 : s_begin + 11, cnt);
     if (s_begin >= s_end) return;
-    const int plane = n1 * n1;
-    float4* const gcol = grid + (j * n1 + k);  // this lane's column of the stencil, relative to the base node
+    const uint32_t plane = (uint32_t) (n1 * n1);
+    const uint32_t col = (uint32_t) (j * n1 + k);  // this lane's column of the stencil, relative to the base node
 
     float2 acc01[3];
     float acc2[3], accm[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
 
+    // one vector reduction per owned node; the accumulators are not cleared: the particle that opens the next run
+    // overwrites them
     auto flush = [&](int node) {
-        float4* dst = gcol + node;
+        const uint32_t idx = (uint32_t) node + col;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            red_add_f32x4(dst + i * plane, make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]));
-            acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
-        }
+        for (int i = 0; i < 3; ++i)
+            red_add_f32x4(grid + (idx + (uint32_t) i * plane), make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]));
     };
 
     const float4* pp = &pkt[warp][s_begin * CH];
-    int cur = __float_as_int(pp[10].w);
+    int cur = -1;
     for (int s = s_begin; s < s_end; ++s, pp += CH) {
         const float4 a = pp[jk], c = pp[9], x = pp[10];
         const int node = __float_as_int(x.w);
-        if (node != cur) {  // a new cell starts: one vector reduction per owned node
-            flush(cur);
-            cur = node;
-        }
         const float w0 = x.x * a.w, w1 = x.y * a.w, w2 = x.z * a.w;
         const float2 q0 = make_float2(a.x, a.y), c01 = make_float2(c.x, c.y);
         const float2 q1 = __fadd2_rn(q0, c01), q2 = ffma2(c01, splat2(2.0f), q0);
         const float z1 = a.z + c.z, z2 = fmaf(c.z, 2.0f, a.z);
-        acc01[0] = ffma2(splat2(w0), q0, acc01[0]), acc2[0] = fmaf(w0, a.z, acc2[0]), accm[0] = fmaf(w0, c.w, accm[0]);
-        acc01[1] = ffma2(splat2(w1), q1, acc01[1]), acc2[1] = fmaf(w1, z1, acc2[1]), accm[1] = fmaf(w1, c.w, accm[1]);
-        acc01[2] = ffma2(splat2(w2), q2, acc01[2]), acc2[2] = fmaf(w2, z2, acc2[2]), accm[2] = fmaf(w2, c.w, accm[2]);
+        if (node != cur) {  // a new cell starts: one vector reduction per owned node, the run restarts from this particle
+            if (cur >= 0) flush(cur);
+            cur = node;
+            acc01[0] = fmul2(splat2(w0), q0), acc2[0] = w0 * a.z, accm[0] = w0 * c.w;
+            acc01[1] = fmul2(splat2(w1), q1), acc2[1] = w1 * z1, accm[1] = w1 * c.w;
+            acc01[2] = fmul2(splat2(w2), q2), acc2[2] = w2 * z2, accm[2] = w2 * c.w;
+        } else {
+            acc01[0] = ffma2(splat2(w0), q0, acc01[0]), acc2[0] = fmaf(w0, a.z, acc2[0]), accm[0] = fmaf(w0, c.w, accm[0]);
+            acc01[1] = ffma2(splat2(w1), q1, acc01[1]), acc2[1] = fmaf(w1, z1, acc2[1]), accm[1] = fmaf(w1, c.w, accm[1]);
+            acc01[2] = ffma2(splat2(w2), q2, acc01[2]), acc2[2] = fmaf(w2, z2, acc2[2]), accm[2] = fmaf(w2, c.w, accm[2]);
+        }
     }
-    flush(cur);
+    if (cur >= 0) flush(cur);
 }
 
 // ---- K2 (variant 4, 3D): variant 3 with three particle STREAMS per warp -------------------------
@@ -325,8 +333,32 @@ __global__ void __launch_bounds__(kP2GWarps * 32, kP2GColsMinB) k_p2g_cols(Parti
 // slots.  Per chunk, lanes [0,11) [11,22) [22,32) load the next 11/11/10 particles of streams 0/1/2
 // (phase A), then group g walks them (phase B) with its run accumulators carried from chunk to chunk:
 // the only flushes left are real cell changes plus three per warp, i.e. 3/C per 32 particles.
-template <int MODEL>
-__global__ void __launch_bounds__(kP2GWarps * 32, kP2GColsMinB) k_p2g_streams(ParticleStore S, const uint32_t* __restrict__ perm,
+// Raw particle rows of one phase-A lane (108 B): loaded one chunk AHEAD, right before the node walk of the current
+// chunk, so that their DRAM latency is covered by phase B instead of stalling the next phase A.
+struct P2GRaw {
+    float4 a0, a1, a2, a3, a4, a5;
+    float c8;
+    float2 mv;
+};
+__device__ __forceinline__ void p2g_load_raw(const ParticleStore& S, uint32_t i, P2GRaw& r) {
+    r.a0 = ldg4(S.q[0] + i), r.a1 = ldg4(S.q[1] + i), r.a2 = ldg4(S.q[2] + i), r.a3 = ldg4(S.q[3] + i);
+    r.a4 = ldg4(S.q[4] + i), r.a5 = ldg4(S.q[5] + i);
+    r.c8 = __ldg(S.s + i);
+    r.mv = __ldg(S.mv + i);
+}
+__device__ __forceinline__ void p2g_unpack_raw(const P2GRaw& r, PState<3>& p) {
+    p.x[0] = r.a0.x, p.x[1] = r.a0.y, p.x[2] = r.a0.z, p.Jp = r.a0.w;
+    p.F.m[0] = r.a1.x, p.F.m[1] = r.a1.y, p.F.m[2] = r.a1.z, p.F.m[3] = r.a1.w;
+    p.F.m[4] = r.a2.x, p.F.m[5] = r.a2.y, p.F.m[6] = r.a2.z, p.F.m[7] = r.a2.w;
+    p.F.m[8] = r.a3.x, p.v[0] = r.a3.y, p.v[1] = r.a3.z, p.v[2] = r.a3.w;
+    p.C.m[0] = r.a4.x, p.C.m[1] = r.a4.y, p.C.m[2] = r.a4.z, p.C.m[3] = r.a4.w;
+    p.C.m[4] = r.a5.x, p.C.m[5] = r.a5.y, p.C.m[6] = r.a5.z, p.C.m[7] = r.a5.w;
+    p.C.m[8] = r.c8;
+    p.mass = r.mv.x, p.volume = r.mv.y;
+}
+
+template <int MODEL, int MINB>
+__global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_streams(ParticleStore S, const uint32_t* __restrict__ perm,
                                                                              uint32_t n, MaterialParams P,
                                                                              float4* __restrict__ grid, int* __restrict__ error_flag,
                                                                              const uint32_t* __restrict__ gone_keys, int chunks) {
@@ -351,8 +383,8 @@ __global__ void __launch_bounds__(kP2GWarps * 32, kP2GColsMinB) k_p2g_streams(Pa
     const int g = lane / 9, jk = lane - 9 * g, j = jk / 3, k = jk - 3 * j;
     const int wb = (g == 2) ? 10 : 11;
     const int len_b = (lane < 27) ? max(0, min(wb * chunks, total - 11 * g * chunks)) : 0;
-    const int plane = n1 * n1;
-    float4* const gcol = grid + (j * n1 + k);
+    const uint32_t plane = (uint32_t) (n1 * n1);
+    const uint32_t col = (uint32_t) (j * n1 + k);  // this lane's stencil column, relative to the base node
 
     float2 acc01[3];
     float acc2[3], accm[3];
@@ -360,22 +392,29 @@ __global__ void __launch_bounds__(kP2GWarps * 32, kP2GColsMinB) k_p2g_streams(Pa
     for (int i = 0; i < 3; ++i) acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
     int cur = -1;
 
+    // one vector reduction per owned node; the accumulators are NOT cleared here: the particle that opens the next
+    // run overwrites them (see the walk below)
     auto flush = [&](int node) {
-        float4* dst = gcol + node;
+        const uint32_t idx = (uint32_t) node + col;  // 32-bit node indices (cells < 2^31): one IMAD.WIDE per address
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            red_add_f32x4(dst + i * plane, make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]));
-            acc01[i] = splat2(0.0f), acc2[i] = 0.0f, accm[i] = 0.0f;
-        }
+        for (int i = 0; i < 3; ++i)
+            red_add_f32x4(grid + (idx + (uint32_t) i * plane), make_float4(acc01[i].x, acc01[i].y, acc2[i], accm[i]));
     };
+
+    // chunk 0's rows; afterwards every chunk's rows are requested while the previous chunk is walked
+    P2GRaw raw;
+    uint32_t slot = 0;
+    bool have = ia < len_a;
+    if (have) {
+        slot = first + (uint32_t) (off_a + ia);
+        p2g_load_raw(S, perm ? __ldg(perm + slot) : slot, raw);
+    }
 
     for (int c = 0; c < chunks; ++c) {
         // ---- phase A (lane = particle of stream ga) ------------------------------------------
-        const int pos = c * wa + ia;
-        if (pos < len_a) {
-            const uint32_t slot = first + (uint32_t) (off_a + pos);
+        if (have) {
             PState<D> p;
-            load_for_p2g<D>(S, perm ? __ldg(perm + slot) : slot, p);
+            p2g_unpack_raw(raw, p);
             int base[D];
             float fx[D], w[D][3];
             if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
@@ -392,8 +431,8 @@ __global__ void __launch_bounds__(kP2GWarps * 32, kP2GColsMinB) k_p2g_streams(Pa
                 float afx = A(r, 0) * fx[0];
 #pragma unroll
                 for (int q = 1; q < D; ++q) afx = fmaf(A(r, q), fx[q], afx);
-                b[r] = fmaf(-P.dx, afx, p.v[r] * p.mass);
-                c0[r] = P.dx * A(r, 0), c1[r] = P.dx * A(r, 1), c2[r] = P.dx * A(r, 2);
+                b[r] = gone ? 0.0f : fmaf(-P.dx, afx, p.v[r] * p.mass);
+                c0[r] = gone ? 0.0f : P.dx * A(r, 0), c1[r] = gone ? 0.0f : P.dx * A(r, 1), c2[r] = gone ? 0.0f : P.dx * A(r, 2);
             }
             float4* my = &pkt[warp][lane * CH];
 #pragma unroll
@@ -414,23 +453,37 @@ __global__ void __launch_bounds__(kP2GWarps * 32, kP2GColsMinB) k_p2g_streams(Pa
         }
         __syncwarp();
 
+        // ---- next chunk's rows: in flight during the node walk below --------------------------------
+        {
+            const int pos = (c + 1) * wa + ia;
+            have = (c + 1 < chunks) && pos < len_a;
+            if (have) {
+                slot = first + (uint32_t) (off_a + pos);
+                p2g_load_raw(S, perm ? __ldg(perm + slot) : slot, raw);
+            }
+        }
+
         // ---- phase B (lane = stream g, stencil column (j,k); nodes i = 0,1,2 in registers) -----
         const int cnt_b = min(wb, len_b - c * wb);  // <= 0 for lanes >= 27 and for exhausted streams
         const float4* pp = &pkt[warp][(11 * g) * CH];
         for (int u = 0; u < cnt_b; ++u, pp += CH) {
             const float4 a = pp[jk], cc = pp[9], x = pp[10];
             const int node = __float_as_int(x.w);
-            if (node != cur) {  // a new cell starts: one vector reduction per owned node
-                if (cur >= 0) flush(cur);
-                cur = node;
-            }
             const float w0 = x.x * a.w, w1 = x.y * a.w, w2 = x.z * a.w;
             const float2 q0 = make_float2(a.x, a.y), c01 = make_float2(cc.x, cc.y);
             const float2 q1 = __fadd2_rn(q0, c01), q2 = ffma2(c01, splat2(2.0f), q0);
             const float z1 = a.z + cc.z, z2 = fmaf(cc.z, 2.0f, a.z);
-            acc01[0] = ffma2(splat2(w0), q0, acc01[0]), acc2[0] = fmaf(w0, a.z, acc2[0]), accm[0] = fmaf(w0, cc.w, accm[0]);
-            acc01[1] = ffma2(splat2(w1), q1, acc01[1]), acc2[1] = fmaf(w1, z1, acc2[1]), accm[1] = fmaf(w1, cc.w, accm[1]);
-            acc01[2] = ffma2(splat2(w2), q2, acc01[2]), acc2[2] = fmaf(w2, z2, acc2[2]), accm[2] = fmaf(w2, cc.w, accm[2]);
+            if (node != cur) {  // a new cell starts: one vector reduction per owned node, then the run restarts from this particle
+                if (cur >= 0) flush(cur);
+                cur = node;
+                acc01[0] = fmul2(splat2(w0), q0), acc2[0] = w0 * a.z, accm[0] = w0 * cc.w;
+                acc01[1] = fmul2(splat2(w1), q1), acc2[1] = w1 * z1, accm[1] = w1 * cc.w;
+                acc01[2] = fmul2(splat2(w2), q2), acc2[2] = w2 * z2, accm[2] = w2 * cc.w;
+            } else {
+                acc01[0] = ffma2(splat2(w0), q0, acc01[0]), acc2[0] = fmaf(w0, a.z, acc2[0]), accm[0] = fmaf(w0, cc.w, accm[0]);
+                acc01[1] = ffma2(splat2(w1), q1, acc01[1]), acc2[1] = fmaf(w1, z1, acc2[1]), accm[1] = fmaf(w1, cc.w, accm[1]);
+                acc01[2] = ffma2(splat2(w2), q2, acc01[2]), acc2[2] = fmaf(w2, z2, acc2[2]), accm[2] = fmaf(w2, cc.w, accm[2]);
+            }
         }
         __syncwarp();  // the packets are overwritten by the next chunk
     }
@@ -451,7 +504,8 @@ inline void launch_p2g_streams(const ParticleStore& S, const uint32_t* perm, uin
         if (chunks <= 0) chunks = p2g_stream_chunks(n);
         const unsigned per_block = kP2GWarps * 32 * chunks;
         const unsigned blocks = (n + per_block - 1) / per_block;
-        k_p2g_streams<MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys, chunks);
+        // 5 CTAs per SM leave 96 registers per thread: the rows of the next chunk stay in registers during the node walk
+        k_p2g_streams<MODEL, kP2GStreamsMinB><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys, chunks);
     } else {  // 2D scenes are launch-bound (cfg1: 5 000 particles): the lane = node kernel stays
         const unsigned blocks = (n + kP2GWarps * 32 - 1) / (kP2GWarps * 32);
         k_p2g_cell<D, MODEL><<<blocks, kP2GWarps * 32, 0, st>>>(S, perm, n, P, grid, error_flag, gone_keys);

@@ -45,7 +45,8 @@ class MaterialModel(enum.IntEnum):
 
 class Options(ct.Structure):
     _fields_ = [("device", ct.c_int), ("sort_every", ct.c_int), ("p2g_variant", ct.c_int), ("use_graph", ct.c_int),
-                ("slab_x0", ct.c_int), ("slab_x1", ct.c_int), ("capacity", ct.c_int), ("reserved", ct.c_int * 9)]
+                ("slab_x0", ct.c_int), ("slab_x1", ct.c_int), ("capacity", ct.c_int), ("g2p_window", ct.c_int),
+                ("reserved", ct.c_int * 8)]
 
 
 def lib_path() -> Path:
@@ -165,7 +166,7 @@ class MPMSimulation:
     def __init__(self, particles, model, res: int = 64, dt: float = 1e-4, E: float = 1e4, nu: float = 0.2,
                  gravity: float = -100.0, *, v=None, F=None, C=None, Jp=None, mass=None, volume=None,
                  device: int = 0, sort_every: int = 4, p2g_variant: int = 0, slab=None, capacity: int = 0,
-                 ids=None):
+                 ids=None, g2p_window: int = 0):
         self._L = load_library()
         x = _f32(particles)
         if x.ndim != 2 or x.shape[1] not in (2, 3):
@@ -175,7 +176,7 @@ class MPMSimulation:
         n, d = self.n, self.dim
         opt = Options()
         self._L.nmpm_default_options(C_byref(opt))
-        opt.device, opt.sort_every, opt.p2g_variant = device, sort_every, p2g_variant
+        opt.device, opt.sort_every, opt.p2g_variant, opt.g2p_window = device, sort_every, p2g_variant, g2p_window
         if slab is not None:
             opt.slab_x0, opt.slab_x1 = slab
             opt.capacity = int(capacity)

@@ -1,0 +1,25 @@
+#!/bin/bash
+# GPU visit: bash tools/gpu_visit.sh <tag> [steps...]   steps: test fullres bench ref snow128 launches ncu cfg5
+tag=${1:-visit}; shift
+what=${@:-test bench}
+out=gpurun_out/$tag
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/nvidia-smi.txt 2>&1
+for w in $what; do
+case $w in
+test)    timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_parity_fullres_gpu.py > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 $out/pytest_gpu.log;;
+fullres) rm -f gpurun_out/parity_fullres.md; timeout 1500 python -m pytest tests/test_parity_fullres_gpu.py -m gpu -q > $out/pytest_fullres.log 2>&1; echo "fullres rc=$?"; tail -15 $out/pytest_fullres.log; cp gpurun_out/parity_fullres.md $out/ 2>/dev/null;;
+smoke)   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $out/smoke.log;;
+bench)   timeout 900 python bench.py --steps 20 --warmup 5 > $out/bench_default.json 2> $out/bench_default.err; echo "bench rc=$?"; tail -3 $out/bench_default.err; python tools/bench_summary.py $out/bench_default.json;;
+quick)   timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu > $out/bench_quick.json 2> $out/bench_quick.err; echo "bench rc=$?"; tail -3 $out/bench_quick.err; python tools/bench_summary.py $out/bench_quick.json;;
+ref)     timeout 1500 python bench.py --impl reference --steps 20 --warmup 5 > $out/bench_ref.json 2> $out/bench_ref.err; echo "ref rc=$?"; cut -c1-1500 $out/bench_ref.json;;
+snow128|cfg1|cfg2|cfg3) timeout 900 python bench.py --workload $w --steps 50 --warmup 5 --no-cpu > $out/bench_$w.json 2> $out/bench_$w.err; echo "bench $w rc=$?"; python tools/bench_summary.py $out/bench_$w.json;;
+launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $out/launches_cfg4.csv \
+            python tools/profile_step.py --workload cfg4 --warmup 28 --steps 8 --sort-every 4 > $out/ncu_launches.log 2>&1; echo "launches rc=$?";;
+ncu)     timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_p2g|k_g2p' -s 56 -c 8 \
+            -f -o $out/prof_cfg4 python tools/profile_step.py --workload cfg4 --warmup 28 --steps 6 --sort-every 4 > $out/ncu_full.log 2>&1; echo "ncu rc=$?"; tail -2 $out/ncu_full.log;;
+cfg5)    timeout 600 python tools/bench_cfg5.py > $out/cfg5.json 2> $out/cfg5.err; echo "cfg5 rc=$?"; cat $out/cfg5.json;;
+*) echo "unknown step $w";;
+esac
+done
+ls $out
