@@ -382,6 +382,7 @@ def main():
                     help="also time K steps starting at this step (late, dispersed phase); -1 = 300 for the 3D snow "
                          "scenes, off otherwise; 0 = off")
     ap.add_argument("--rebalance-every", type=int, default=50, help="multi-GPU: re-balance slab boundaries every k steps")
+    ap.add_argument("--no-verify", action="store_true", help="multi-GPU: skip the 3-step comparison with a single-GPU twin")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
     if args.late_step < 0:

@@ -194,6 +194,11 @@ int nmpm_slab_comm_init(nmpm_handle h, const void *unique_id128, int rank, int w
 int nmpm_slab_step(nmpm_handle h, int nsteps);
 int nmpm_slab_set_bounds(nmpm_handle h, const int *bounds);
 long long nmpm_slab_migrated(nmpm_handle h);
+/* A sim driven by nmpm_slab_step keeps its particle counts on the device (the host only holds an upper bound of the
+ * slots in use, so that no step waits for the host): true counts, synchronising the stream.  nmpm_num_particles
+ * returns the same `particles`; nmpm_num_slots the host's bound (slots beyond the true count report id 0xFFFFFFFF
+ * in nmpm_download_particles_slots, like migrated-away ones). */
+int nmpm_slab_counts(nmpm_handle h, long long *particles, long long *slots_in_use);
 /* global ids for the slab's particles (host array of n, creation order); particles() of the global
  * simulation is assembled from nmpm_download_particles_slots by scattering on ids */
 int nmpm_set_ids(nmpm_handle h, const uint32_t *ids);

@@ -70,7 +70,10 @@ struct nmpm_sim {
     bool local_reorder = true;  // in-place G2P re-groups each warp's 32 slots by cell key (NMPM_LOCAL_REORDER=0: off)
     CUtensorMap grid_map{};     // 3D: the grid as a rank-4 tensor {4 floats, z, y, x} with one x-plane window box (G2P)
     bool g2p_window = false;    // 3D: G2P stages its node window through the TMA (NMPM_G2P_WINDOW=0: off)
-    bool p2g_early = false;   // slab mode: the in-place P2G of the coming step was issued before the migrants arrived
+    // device-driven slab step (nmpm_slab_comm.inl): the true slot / gone counts live in d_ctr, `n_store` is only an upper
+    // bound for launch sizes, every slot beyond the true count (and every migrated-away slot) carries kKeyGone in keys_a
+    bool dev_counts = false;
+    int* d_ctr = nullptr;
     bool grid_valid = false;  // false until the first p2g: the reference's grid() is empty (src/solver.cpp:52-57)
 
     SortWorkspace sort;
@@ -328,6 +331,13 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
     CUDA_TRY(h, cudaMalloc(&h->sort.digit_base, kRadix * sizeof(uint32_t)));
     CUDA_TRY(h, cudaMalloc(&h->sort.done_counter, sizeof(unsigned int)));
     CUDA_TRY(h, cudaMemset(h->sort.done_counter, 0, sizeof(unsigned int)));
+    if (h->slab) {  // unused slots read as "migrated away" until a particle is appended there
+        CUDA_TRY(h, cudaMemset(h->sort.keys_a, 0xFF, nn * sizeof(uint32_t)));
+        CUDA_TRY(h, cudaMemset(h->sort.keys_b, 0xFF, nn * sizeof(uint32_t)));
+        CUDA_TRY(h, cudaMalloc(&h->d_ctr, 4 * sizeof(int)));
+        const int ctr0[4] = {(int) n, 0, 0, 0};
+        CUDA_TRY(h, cudaMemcpy(h->d_ctr, ctr0, sizeof(ctr0), cudaMemcpyHostToDevice));
+    }
     for (auto& e : h->ev) CUDA_TRY(h, cudaEventCreate(&e));
     return NMPM_OK;
 }
@@ -363,6 +373,7 @@ void nmpm_destroy(nmpm_handle h) {
     if (h->d_box) cudaFree(h->d_box);
     if (h->d_box_partial) cudaFree(h->d_box_partial);
     if (h->d_error) cudaFree(h->d_error);
+    if (h->d_ctr) cudaFree(h->d_ctr);
     if (h->h_error) cudaFreeHost(h->h_error);
     if (h->staging) cudaFree(h->staging);
     cudaFree(h->sort.keys_a);
@@ -482,7 +493,14 @@ int nmpm_create_aos(int dim, int model, int res, float dt, float E, float nu, fl
     return NMPM_OK;
 }
 
-size_t nmpm_num_particles(nmpm_handle h) { return h ? h->n_store - h->n_gone : 0; }
+size_t nmpm_num_particles(nmpm_handle h) {
+    if (!h) return 0;
+    if (h->dev_counts) {  // device-driven slab: the host only holds a bound; read the counters (synchronises)
+        long long np = 0;
+        return nmpm_slab_counts(h, &np, nullptr) == NMPM_OK ? (size_t) np : 0;
+    }
+    return h->n_store - h->n_gone;
+}
 size_t nmpm_grid_cells(nmpm_handle h) { return h ? h->cells : 0; }
 size_t nmpm_num_slots(nmpm_handle h) { return h ? h->n_store : 0; }
 int nmpm_key_tile_bits(nmpm_handle) { return kTileBits; }
@@ -531,6 +549,16 @@ static int do_sort(nmpm_sim* h) {
     h->launches += radix_sort_pairs(h->sort, n, h->key_bits, h->stream, &ks, &perm);
     h->keys_valid = false;
     h->perm = perm;
+    if (h->dev_counts) {
+        // the sorted order ends with the migrated-away and the unused slots; they are skipped through their sorted keys,
+        // which must sit in keys_a (the buffer G2P writes the next keys into, slot by slot)
+        if (ks != h->sort.keys_a)
+            CUDA_TRY(h, cudaMemcpyAsync(h->sort.keys_a, ks, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+        k_ctr_after_sort<<<1, 32, 0, h->stream>>>(h->d_ctr);
+        h->launches++;
+        h->n = h->n_store;
+        return NMPM_OK;
+    }
     // slab mode: particles that migrated away carry kKeyGone and sort last; they drop out here
     h->n = h->n_store - h->n_gone;
     h->n_gone = 0;
@@ -574,7 +602,7 @@ static int do_p2g(nmpm_sim* h) {
     const uint32_t n = (uint32_t) h->n;
     ParticleStore& S = h->store[h->cur];
     // slab mode, step without a sort: slots of migrated-away particles are still in the store
-    const uint32_t* gone_keys = (h->slab && !h->perm && (h->n_gone || h->p2g_early)) ? h->sort.keys_a : nullptr;
+    const uint32_t* gone_keys = (h->dev_counts || (h->slab && !h->perm && h->n_gone)) ? h->sort.keys_a : nullptr;
     int variant = h->opt.p2g_variant;
     // auto: per-particle reductions without binning; with binning the per-column-packet kernel, on three streams per
     // warp once the scene is large enough for the reductions to miss L2 (measured: profiles/r01g)
@@ -616,7 +644,7 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
     const bool next_sorts = h->opt.sort_every > 0 && ((h->steps_done + 1) % h->opt.sort_every) == 0;
     // a slab keeps the key array aligned with the slots at all times: it carries the "migrated away" marks
     uint32_t* keys_out = (next_sorts || h->slab) ? h->sort.keys_a : nullptr;
-    const uint32_t* gone_keys = (h->slab && !h->perm && (h->n_gone || h->p2g_early)) ? h->sort.keys_a : nullptr;
+    const uint32_t* gone_keys = (h->dev_counts || (h->slab && !h->perm && h->n_gone)) ? h->sort.keys_a : nullptr;
     const int box_next = (h->box_cur + 1) % kBoxRing;
     k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + box_next);
     if (h->g2p_window) {  // 3D only (set at creation)
@@ -1136,28 +1164,6 @@ int nmpm_slab_p2g(nmpm_handle h) {
 
 }  // extern "C"
 
-// Native slab step only (nmpm_slab_comm.inl): issue the coming step's in-place P2G over the resident slots while the
-// host still waits for the migration table, then scatter the received particles (slots [first_new, n_store)) on top.
-static bool slab_next_step_in_place(const nmpm_sim* h) {
-    return h->slab && !h->timing && h->keys_valid && h->opt.sort_every > 0 && (h->steps_done % h->opt.sort_every) != 0;
-}
-static int slab_p2g_early(nmpm_sim* h) {
-    h->p2g_early = true;  // before nmpm_slab_p2g: its P2G must honour the gone marks although n_gone is not updated yet
-    return nmpm_slab_p2g(h);
-}
-static int slab_p2g_tail(nmpm_sim* h, size_t first_new) {
-    if (h->n_store > first_new) {
-        const uint32_t n = (uint32_t) h->n_store, first = (uint32_t) first_new;
-        NMPM_DISPATCH(h, (k_p2g_scatter<D, MODEL><<<blocks_for(n - first, 128), 128, 0, h->stream>>>(
-                             h->store[h->cur], nullptr, n, h->P, h->grid, h->d_error, nullptr, first)));
-        h->launches++;
-    }
-    h->n = h->n_store;  // grid_op / G2P of this step run over every slot
-    h->p2g_early = false;
-    CUDA_TRY(h, cudaGetLastError());
-    return NMPM_OK;
-}
-
 extern "C" {
 
 int nmpm_slab_grid_g2p(nmpm_handle h, void* send_left, void* send_right, size_t cap_records, int* d_counts) {
@@ -1173,7 +1179,7 @@ int nmpm_slab_grid_g2p(nmpm_handle h, void* send_left, void* send_right, size_t 
     if (int rc = do_grid_op(h)) return rc;
     if (h->timing) cudaEventRecord(h->ev[3], h->stream);
     MigrateArgs mig{h->opt.slab_x0, h->opt.slab_x1, (float*) send_left, (float*) send_right, (uint32_t) cap_records,
-                    d_counts};
+                    d_counts, (uint32_t) cap_records};
     if (int rc = do_g2p(h, mig)) return rc;
     if (h->timing) {  // per-phase device times of this slab (the ghost exchange between P2G and grid_op is not included)
         cudaEventRecord(h->ev[4], h->stream);
@@ -1200,7 +1206,7 @@ int nmpm_slab_unpack(nmpm_handle h, const void* recv_left, size_t n_from_left, c
                      size_t n_from_right, size_t n_sent) {
     if (int rc = slab_check(h, "nmpm_slab_unpack")) return rc;
     if ((n_from_left && !recv_left) || (n_from_right && !recv_right) || n_sent > h->n_store) return NMPM_ERR_INVALID;
-    if (h->phase_next != 0 && !h->p2g_early) {
+    if (h->phase_next != 0) {
         h->last_error = "nmpm_slab_unpack: must follow nmpm_slab_grid_g2p";
         return NMPM_ERR_INVALID;
     }
@@ -1245,7 +1251,7 @@ int nmpm_slab_histogram(nmpm_handle h, int* d_hist) {
     if (h->n_store == 0) return NMPM_OK;
     NMPM_DISPATCH_DIM(h, (k_histogram_x<D><<<blocks_for(h->n_store, 256), 256, 0, h->stream>>>(
                              h->store[h->cur], (uint32_t) h->n_store, h->P, d_hist,
-                             h->n_gone ? h->sort.keys_a : nullptr)));
+                             (h->n_gone || h->dev_counts) ? h->sort.keys_a : nullptr)));
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return NMPM_OK;
@@ -1293,7 +1299,7 @@ int nmpm_download_particles_slots(nmpm_handle h, float* x, float* v, float* F, f
         uint32_t* did = (uint32_t*) p;
         NMPM_DISPATCH_DIM(h, (k_export_soa<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(h->store[h->cur], (uint32_t) n,
                                                                                          dx, dv, dF, dC, dJ, did,
-                                                                                         h->n_gone ? h->sort.keys_a : nullptr)));
+                                                                                         (h->n_gone || h->dev_counts) ? h->sort.keys_a : nullptr)));
         h->launches++;
         if (x) CUDA_TRY(h, cudaMemcpyAsync(x, dx, n * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         if (v) CUDA_TRY(h, cudaMemcpyAsync(v, dv, n * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));

@@ -46,8 +46,9 @@ struct MigrateArgs {
     int x0, x1;
     float* left;
     float* right;
-    uint32_t cap;
-    int* counts;  // {n_left, n_right, n_kept, overflow}
+    uint32_t cap;     // records the left buffer holds
+    int* counts;      // {n_left, n_right, n_kept, overflow}
+    uint32_t cap_right = 0;  // records the right buffer holds
 };
 
 template <int D>
@@ -514,7 +515,9 @@ __device__ __forceinline__ void g2p_finish(PState<D>& p, const Mat<D>& Cn, const
                                            int tiles_per_axis, const MigrateArgs& mig, int* __restrict__ box_partial,
                                            const uint32_t* __restrict__ gone_keys, int local_reorder) {
     g2p_update<D, MODEL>(p, Cn, vn, P);
-    const bool reorder = local_reorder && !mig.left && !gone_keys;  // warp-uniform (kernel arguments); single GPU only
+    // warp-uniform (kernel argument).  Slabs re-group as well: ranks are mapped onto the slots of the warp's LIVE lanes
+    // (slots whose particle migrated away keep their "gone" mark and stay where they are).
+    const bool reorder = local_reorder != 0;
     {   // bin the advected particle for the NEXT step: cell key, slab owner, node box
         int b[D];
         bool bad = false;
@@ -563,7 +566,9 @@ __device__ __forceinline__ void g2p_finish(PState<D>& p, const Mat<D>& Cn, const
                     eq &= ~ones;
                 }
             }
-            dst = (i - lane) + (uint32_t) (__popc(lt) + __popc(peers & ((1u << lane) - 1u)));
+            const int rank = __popc(lt) + __popc(peers & ((1u << lane) - 1u));
+            // the rank-th live slot of the warp (all 32 lanes live: the rank itself)
+            dst = (i - lane) + (uint32_t) ((live == 0xffffffffu) ? rank : (int) __fns(live, 0, rank + 1));
             __syncwarp(live);  // T == S: every lane has read its old slot (state, mass/volume, id) before any is overwritten
         }
         store_state<D>(T, dst, p);
@@ -575,7 +580,7 @@ __device__ __forceinline__ void g2p_finish(PState<D>& p, const Mat<D>& Cn, const
         if (mig.left && !bad && (b[0] < mig.x0 || b[0] >= mig.x1)) {
             const int side = (b[0] < mig.x0) ? 0 : 1;
             const uint32_t slot = (uint32_t) atomicAdd(mig.counts + side, 1);
-            if (slot < mig.cap) {
+            if (slot < (side ? mig.cap_right : mig.cap)) {
                 write_record<D>((side ? mig.right : mig.left) + (size_t) slot * RecordTraits<D>::WORDS, p, mv, pid);
                 key = kKeyGone;
                 gone = true;
@@ -773,6 +778,98 @@ __global__ void __launch_bounds__(256) k_unpack_records(const float* __restrict_
 #pragma unroll
     for (int d = 0; d < D; ++d) b[d] = min(max(b[d], 0), P.res - 2);
     box_update<D>(box, b, true);
+}
+
+// ---- device-driven slab step (nmpm_slab_comm.inl): particle counts live on the device ------------------------------
+// ctr[0] = slots in use in the current store (true value; the host only keeps an upper bound for launch sizes),
+// ctr[1] = slots whose particle migrated away since the last sort, ctr[2] = error bits (1: store capacity exceeded)
+//
+// A migrant message is [header record][records ...]; header ints: [0] count, [1..3] lo, [4..6] hi of the sender's node
+// box for the coming step, [7] the sender's step number.
+constexpr int kHdrInts = 8;
+
+// after G2P: headers of the two outgoing messages, gone count
+template <int D>
+__global__ void k_slab_headers(const int* __restrict__ counts /* n_left, n_right, n_kept, overflow */, const GridBox* __restrict__ box,
+                               int* __restrict__ hdr_left, int* __restrict__ hdr_right, int* __restrict__ ctr, int step,
+                               int* __restrict__ ring) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int nl = counts[0], nr = counts[1];
+    int* h[2] = {hdr_left, hdr_right};
+    for (int s = 0; s < 2; ++s) {
+        h[s][0] = s ? nr : nl;
+        for (int d = 0; d < 3; ++d) h[s][1 + d] = box->lo[d], h[s][4 + d] = box->hi[d];
+        h[s][7] = step;
+    }
+    ctr[1] += nl + nr;
+    if (counts[3]) ctr[2] |= 2;  // a send buffer overflowed
+    // read-back record of this step, first part: counts + box
+    for (int k = 0; k < 4; ++k) ring[k] = counts[k];
+    for (int d = 0; d < 3; ++d) ring[4 + d] = box->lo[d], ring[7 + d] = box->hi[d];
+    ring[10] = step, ring[11] = 0;
+}
+
+// receiving side: append the records of both neighbours behind slot ctr[0] and bin them; counts come from the headers
+template <int D>
+__global__ void __launch_bounds__(256) k_unpack_records2(const float* __restrict__ rec_left, const float* __restrict__ rec_right,
+                                                         uint32_t cap_msg_left, uint32_t cap_msg_right, uint32_t cap_store,
+                                                         ParticleStore T, MaterialParams P, int tiles_per_axis,
+                                                         uint32_t* __restrict__ keys, GridBox* __restrict__ box, int* __restrict__ ctr) {
+    constexpr int W = RecordTraits<D>::WORDS;
+    const uint32_t cl = rec_left ? min((uint32_t) __float_as_int(__ldg(rec_left)), cap_msg_left) : 0u;
+    const uint32_t cr = rec_right ? min((uint32_t) __float_as_int(__ldg(rec_right)), cap_msg_right) : 0u;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cl + cr) return;
+    const uint32_t first = (uint32_t) ctr[0];  // not modified by this kernel (k_ctr_after_unpack follows)
+    const uint32_t i = first + j;
+    if (i >= cap_store) {
+        atomicOr(ctr + 2, 1);
+        return;
+    }
+    const float* r = (j < cl) ? rec_left + (size_t) (1 + j) * W : rec_right + (size_t) (1 + j - cl) * W;
+    PState<D> p;
+#pragma unroll
+    for (int d = 0; d < D; ++d) p.x[d] = r[d], p.v[d] = r[D + d];
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) p.F.m[k] = r[2 * D + k], p.C.m[k] = r[2 * D + D * D + k];
+    p.Jp = r[2 * D + 2 * D * D];
+    store_state<D>(T, i, p);
+    T.mv[i] = make_float2(r[2 * D + 2 * D * D + 1], r[2 * D + 2 * D * D + 2]);
+    T.id[i] = __float_as_uint(r[2 * D + 2 * D * D + 3]);
+    int b[D];
+    bool bad = false;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const Stencil1 s = stencil_axis(p.x[d], P.inv_dx, P.res);
+        b[d] = s.base;
+        bad = bad || !s.ok;
+    }
+    keys[i] = bad ? kKeyOutOfGrid : cell_key<D>(b, tiles_per_axis);
+#pragma unroll
+    for (int d = 0; d < D; ++d) b[d] = min(max(b[d], 0), P.res - 2);
+    box_update<D>(box, b, true);
+}
+
+__global__ void k_ctr_after_unpack(const float* __restrict__ rec_left, const float* __restrict__ rec_right, uint32_t cap_msg_left,
+                                   uint32_t cap_msg_right, uint32_t cap_store, int* __restrict__ ctr, int* __restrict__ ring) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint32_t cl = rec_left ? min((uint32_t) __float_as_int(rec_left[0]), cap_msg_left) : 0u;
+    const uint32_t cr = rec_right ? min((uint32_t) __float_as_int(rec_right[0]), cap_msg_right) : 0u;
+    const uint32_t n = min((uint32_t) ctr[0] + cl + cr, cap_store);
+    ctr[0] = (int) n;
+    // read-back record, second part: the two received headers and the counters
+    for (int k = 0; k < kHdrInts; ++k) {
+        ring[12 + k] = rec_left ? __float_as_int(rec_left[k]) : 0;
+        ring[20 + k] = rec_right ? __float_as_int(rec_right[k]) : 0;
+    }
+    for (int k = 0; k < 4; ++k) ring[28 + k] = ctr[k];
+}
+
+// after a sort: the migrated-away slots have dropped to the end of the order and out of the count
+__global__ void k_ctr_after_sort(int* __restrict__ ctr) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ctr[0] -= ctr[1];
+    ctr[1] = 0;
 }
 
 // sub-rectangle of `planes` consecutive node planes: a = slow in-plane axis (y in 3D, none in 2D),

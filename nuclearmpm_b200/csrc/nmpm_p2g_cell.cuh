@@ -77,7 +77,11 @@ __global__ void __launch_bounds__(kP2GWarps * 32, NMPM_P2G_MINB) k_p2g_cell(Part
         for (int k = 0; k <= PK::NV; ++k) vals[k] = 0.0f;
 #pragma unroll
         for (int d = 0; d < D; ++d) w[d][0] = w[d][1] = w[d][2] = 0.0f;
-        if (lane < cnt) {
+        // slab mode: a slot whose particle migrated away (or that was never filled) keeps the all-zero packet and
+        // node -2 (its rows are never read); -1 marks the padding slot of an odd tail
+        const bool gone = lane < cnt && gone_keys && __ldg(gone_keys + first + lane) == kKeyGone;
+        if (gone) nd = -2;
+        if (lane < cnt && !gone) {
             PState<D> p;
             // `perm` (nullable): the store is read THROUGH the sorted permutation, no reorder pass
             load_for_p2g<D>(S, perm ? __ldg(perm + first + lane) : first + lane, p);
@@ -85,21 +89,14 @@ __global__ void __launch_bounds__(kP2GWarps * 32, NMPM_P2G_MINB) k_p2g_cell(Part
             float fx[D];
             if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
             const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, p.mass, p.volume, P);
-            // slab mode between sorts: a slot whose particle migrated away scatters exact zeros
-            const bool gone = gone_keys && __ldg(gone_keys + first + lane) == kKeyGone;
-            if (gone) {
-                p.mass = 0.0f;
-#pragma unroll
-                for (int d = 0; d < D; ++d) w[d][0] = w[d][1] = w[d][2] = 0.0f;
-            }
 #pragma unroll
             for (int r = 0; r < D; ++r) {
                 float afx = A(r, 0) * fx[0];
 #pragma unroll
                 for (int k = 1; k < D; ++k) afx = fmaf(A(r, k), fx[k], afx);
-                vals[r] = gone ? 0.0f : fmaf(-P.dx, afx, p.v[r] * p.mass);  // b_r
+                vals[r] = fmaf(-P.dx, afx, p.v[r] * p.mass);  // b_r
 #pragma unroll
-                for (int c = 0; c < D; ++c) vals[D + r * D + c] = gone ? 0.0f : P.dx * A(r, c);  // A'_rc (row-major here)
+                for (int c = 0; c < D; ++c) vals[D + r * D + c] = P.dx * A(r, c);  // A'_rc (row-major here)
             }
             vals[D + D * D] = p.mass;
             nd = base[0] * n1 + base[1];
@@ -146,7 +143,8 @@ __global__ void __launch_bounds__(kP2GWarps * 32, NMPM_P2G_MINB) k_p2g_cell(Part
         float mom[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) mom[d] = acc[d].x + acc[d].y;
-        red_add_f32x4(grid + (size_t) (node + lane_off), node_pack<D>(mom, acc_m.x + acc_m.y));
+        if (node >= 0)  // a negative node is the (all-zero) run of a migrated-away slot
+            red_add_f32x4(grid + (size_t) (node + lane_off), node_pack<D>(mom, acc_m.x + acc_m.y));
 #pragma unroll
         for (int d = 0; d < D; ++d) acc[d] = splat2(0.0f);
         acc_m = splat2(0.0f);
@@ -235,20 +233,20 @@ __global__ void __launch_bounds__(kP2GWarps * 32, kP2GColsMinB) k_p2g_cols(Parti
     const int n1 = P.n1;
 
     // ---- phase A (lane = particle) ----------------------------------------------------------
-    if (lane < cnt) {
+    // slab mode: a slot whose particle migrated away (or that was never filled) leaves an all-zero packet with node -1
+    const bool gone = lane < cnt && gone_keys && __ldg(gone_keys + first + lane) == kKeyGone;
+    if (gone) {
+        float4* my = &pkt[warp][lane * CH];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) my[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        my[10] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+    } else if (lane < cnt) {
         PState<D> p;
         load_for_p2g<D>(S, perm ? __ldg(perm + first + lane) : first + lane, p);
         int base[D];
         float fx[D], w[D][3];
         if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
         const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, p.mass, p.volume, P);
-        // slab mode between sorts: a slot whose particle migrated away scatters exact zeros
-        const bool gone = gone_keys && __ldg(gone_keys + first + lane) == kKeyGone;
-        if (gone) {
-            p.mass = 0.0f;
-#pragma unroll
-            for (int d = 0; d < D; ++d) w[d][0] = w[d][1] = w[d][2] = 0.0f;
-        }
         float b[D], c0[D], c1[D], c2[D];
 #pragma unroll
         for (int r = 0; r < D; ++r) {
@@ -402,37 +400,39 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_streams(ParticleSt
     };
 
     // chunk 0's rows; afterwards every chunk's rows are requested while the previous chunk is walked
+    // Slab mode: a slot whose particle migrated away, or that was never filled, carries kKeyGone; it leaves an all-zero
+    // packet with node -1 (its rows are never read: they may be uninitialised memory) — a run is cut there, nothing is added.
     P2GRaw raw;
     uint32_t slot = 0;
-    bool have = ia < len_a;
+    bool have = ia < len_a, gone = false;
     if (have) {
         slot = first + (uint32_t) (off_a + ia);
-        p2g_load_raw(S, perm ? __ldg(perm + slot) : slot, raw);
+        gone = gone_keys && __ldg(gone_keys + slot) == kKeyGone;
+        if (!gone) p2g_load_raw(S, perm ? __ldg(perm + slot) : slot, raw);
     }
 
     for (int c = 0; c < chunks; ++c) {
         // ---- phase A (lane = particle of stream ga) ------------------------------------------
-        if (have) {
+        if (have && gone) {
+            float4* my = &pkt[warp][lane * CH];
+#pragma unroll
+            for (int q = 0; q < 10; ++q) my[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            my[10] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+        } else if (have) {
             PState<D> p;
             p2g_unpack_raw(raw, p);
             int base[D];
             float fx[D], w[D][3];
             if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
             const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, p.mass, p.volume, P);
-            const bool gone = gone_keys && __ldg(gone_keys + slot) == kKeyGone;
-            if (gone) {  // slab mode between sorts: a slot whose particle migrated away scatters exact zeros
-                p.mass = 0.0f;
-#pragma unroll
-                for (int d = 0; d < D; ++d) w[d][0] = w[d][1] = w[d][2] = 0.0f;
-            }
             float b[D], c0[D], c1[D], c2[D];
 #pragma unroll
             for (int r = 0; r < D; ++r) {
                 float afx = A(r, 0) * fx[0];
 #pragma unroll
                 for (int q = 1; q < D; ++q) afx = fmaf(A(r, q), fx[q], afx);
-                b[r] = gone ? 0.0f : fmaf(-P.dx, afx, p.v[r] * p.mass);
-                c0[r] = gone ? 0.0f : P.dx * A(r, 0), c1[r] = gone ? 0.0f : P.dx * A(r, 1), c2[r] = gone ? 0.0f : P.dx * A(r, 2);
+                b[r] = fmaf(-P.dx, afx, p.v[r] * p.mass);
+                c0[r] = P.dx * A(r, 0), c1[r] = P.dx * A(r, 1), c2[r] = P.dx * A(r, 2);
             }
             float4* my = &pkt[warp][lane * CH];
 #pragma unroll
@@ -457,9 +457,11 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_streams(ParticleSt
         {
             const int pos = (c + 1) * wa + ia;
             have = (c + 1 < chunks) && pos < len_a;
+            gone = false;
             if (have) {
                 slot = first + (uint32_t) (off_a + pos);
-                p2g_load_raw(S, perm ? __ldg(perm + slot) : slot, raw);
+                gone = gone_keys && __ldg(gone_keys + slot) == kKeyGone;
+                if (!gone) p2g_load_raw(S, perm ? __ldg(perm + slot) : slot, raw);
             }
         }
 

@@ -114,6 +114,7 @@ def load_library():
     sig("nmpm_slab_step", ci, [vp, ci])
     sig("nmpm_slab_set_bounds", ci, [vp, _i32p])
     sig("nmpm_slab_migrated", ct.c_longlong, [vp])
+    sig("nmpm_slab_counts", ci, [vp, ct.POINTER(ct.c_longlong), ct.POINTER(ct.c_longlong)])
     sig("nmpm_set_ids", ci, [vp, _u32p])
     sig("nmpm_download_particles_slots", ci, [vp] + [_fp] * 5 + [_u32p])
     sig("nmpm_num_slots", sz, [vp])

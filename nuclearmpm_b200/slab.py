@@ -224,7 +224,8 @@ class SlabSimulation:
         n_local = len(mine)
         # room for migrants and for drift of the balance between re-balancing steps
         self.capacity = int(n_local * (1.0 + slack)) + 65536
-        self.cap_records = int(n_local * 0.25) + 65536
+        # migrant message capacity: the SAME on every rank (the native step sizes its fixed-capacity messages from it)
+        self.cap_records = int(self.n_global / self.world * 0.25) + 65536
         sub = {k: (None if v is None else np.ascontiguousarray(v)[mine]) for k, v in state.items()}
         factory = engine_factory or GpuSlabEngine
         self.engine = factory(x[mine], mine.astype(np.uint32), int(model), int(res), dt, E, nu, gravity, (x0, x1),
@@ -396,14 +397,63 @@ class SlabSimulation:
 # ------------------------------------------------------------------------------------------------
 # bench.py --gpus N
 # ------------------------------------------------------------------------------------------------
+def verify_slabs(x, model, res, rank, world, local, steps=3):
+    """Correctness of the partitioned step, checked in the bench run itself: a sub-block of the scene (<= 128^3 particles,
+    same spacing / material / grid) is advanced `steps` steps by all `world` slabs and by a single-GPU twin on rank 0;
+    the gathered slab state must hold every particle exactly once and agree with the twin within the tolerances of
+    tests/test_parity_gpu.py::test_full_size_properties_config4 (summation order differs across the slab cut).
+    3 steps: 3D snow decorrelates at step 4 (Q1)."""
+    import torch.distributed as dist
+    from . import sim as _s
+    dim = x.shape[1]
+    n_sub = min(len(x), 128 ** 3)
+    # a contiguous x-major prefix of the block keeps its spacing; trim to whole x-layers of the cube so it stays a block
+    side = round(len(x) ** (1.0 / dim))
+    if side ** dim == len(x) and n_sub < len(x):
+        layers = max(1, n_sub // side ** (dim - 1))
+        xs = np.ascontiguousarray(x[:layers * side ** (dim - 1)])
+    else:
+        xs = np.ascontiguousarray(x[:n_sub])
+    sl = SlabSimulation(xs, model, res, device=local, rebalance_every=2)
+    sl.advance(steps)
+    got = sl.particles(dst=0)           # raises if a particle was lost or duplicated
+    n_sum = int(_all_sum(sl.num_local(), local))
+    out = {"particles": int(len(xs)), "steps": steps, "sum_num_local": n_sum, "migrated_records": int(_all_sum(sl.migrated, local))}
+    del sl
+    if rank == 0:
+        twin = _s.MPMSimulation(xs, model, res, device=local)
+        twin.advance(steps)
+        ref = twin.particles()
+        del twin
+        vmax = max(1.0, float(np.abs(ref["v"]).max()))
+        dv = np.abs(got["v"] - ref["v"]).max(axis=1)
+        out.update(max_dx=float(np.abs(got["x"] - ref["x"]).max()), median_dv_over_vmax=float(np.median(dv)) / vmax,
+                   p999_dv_over_vmax=float(np.quantile(dv, 0.999)) / vmax, max_dJp=float(np.abs(got["Jp"] - ref["Jp"]).max()),
+                   max_dF=float(np.abs(got["F"] - ref["F"]).max()))
+        ok = (n_sum == len(xs) and out["max_dx"] <= 3e-5 and out["median_dv_over_vmax"] <= 1e-3 and
+              out["p999_dv_over_vmax"] <= 5e-3)
+        out["ok"] = bool(ok)
+    dist.barrier()
+    return out
+
+
+def _all_sum(v, local):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(v)], device=torch.device("cuda", local), dtype=torch.float64)
+    dist.all_reduce(t)
+    return float(t[0])
+
+
 def bench_slabs(args, x, model, res, desc, rank, world, local):
     """Strong-scaling bench of one scene across `world` GPUs.  Device time = CUDA events around the step loop
     on each rank, bracketed by barrier + synchronize, MAX over ranks."""
     import torch
     import torch.distributed as dist
-    from bench import ClockSampler, measured_peak_gbs  # noqa: F401
+    from bench import ClockSampler, bench_config, measured_peak_gbs  # noqa: F401
 
     torch.cuda.set_device(local)
+    verification = None if getattr(args, "no_verify", False) else verify_slabs(x, model, res, rank, world, local)
     sim = SlabSimulation(x, model, res, device=local, rebalance_every=args.rebalance_every)
     n_total = len(x)
 
@@ -459,19 +509,33 @@ def bench_slabs(args, x, model, res, desc, rank, world, local):
     t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     d2h = sum(v.nbytes for v in local_state.values())
+    # ---- bookkeeping checks on the state the timed steps left behind: every particle exactly once -----------------
+    ids = local_state["ids"]
+    live = ids[ids != 0xFFFFFFFF].astype(np.uint64)
+    chk = torch.tensor([float(len(live)), float(live.sum()), float((live * live % np.uint64(1000003)).sum())],
+                       device="cuda", dtype=torch.float64)
+    dist.all_reduce(chk)
+    idx = np.arange(n_total, dtype=np.uint64)
+    want = [float(n_total), float(idx.sum()), float((idx * idx % np.uint64(1000003)).sum())]
+    nl = torch.tensor([float(sim.num_local())], device="cuda", dtype=torch.float64)
+    dist.all_reduce(nl)
+    checks = {"sum_num_local": int(nl[0]), "live_slots": int(chk[0]), "id_sum_ok": bool(chk[1] == want[1]),
+              "id_square_hash_ok": bool(chk[2] == want[2]),
+              "ok": bool(int(nl[0]) == n_total and int(chk[0]) == n_total and chk[1] == want[1] and chk[2] == want[2])}
     if rank != 0:
         return None
+    if not checks["ok"] or (verification is not None and not verification.get("ok", False)):
+        raise RuntimeError(f"slab bench: correctness checks failed: {checks} {verification}")
     dim = x.shape[1]
     return {
         "metric": "particle-steps/s", "value": n_total * args.steps / (ms * 1e-3), "unit": "particle-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "particles": int(n_total), "grid_res": res, "dim": dim,
-                   "material": ["snow", "jelly", "liquid"][model], "partition": f"{world} x-slabs by particle count",
-                   "bounds": sim.bounds, "rebalance_every": args.rebalance_every,
-                   "particles_per_rank_min_max": [int(tmin[2]), int(tmax[2])],
-                   "migrated_records_total": int(tsum[3]),
-                   "l2_policy": "inputs larger than L2 (particle store + grid >> 126 MB)"},
+        "config": bench_config(args, desc, n_total, res, dim, model),
+        "run": {"partition": f"{world} x-slabs by particle count", "bounds": sim.bounds,
+                "rebalance_every": args.rebalance_every, "particles_per_rank_min_max": [int(tmin[2]), int(tmax[2])],
+                "migrated_records_total": int(tsum[3])},
+        "checks": checks, "verification": verification,
         "clocks": clocks, "gpu_launches": int(tsum[1]),
         "e2e": {"value": n_total * e2e_steps / float(t_e2e[0]), "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,

@@ -29,14 +29,20 @@ def moving_block(dim, res):
     return x, v
 
 
-def check(got, ref, k, res):
+def check(got, ref, k, res, model=None):
+    """k steps free-running.  At res 512 the rounding of the polar factor is amplified by the stress prefactor
+    (tests/test_parity_fullres_gpu.py: amp = dt vol 4/dx^2 2 mu dx); below that the golden-scene tolerances hold."""
     vmax = max(1.0, float(np.abs(ref["v"]).max()))
     cmax = max(1.0, float(np.abs(ref["C"]).max()))
-    assert np.abs(got["x"] - ref["x"]).max() <= 2.4e-7 * k
-    assert np.abs(got["v"] - ref["v"]).max() <= 1e-5 * vmax * k
-    assert np.abs(got["F"] - ref["F"]).max() <= 2e-5 * k
-    assert np.abs(got["C"] - ref["C"]).max() <= (5e-5 * cmax + 1e-6 * 4 * res * vmax) * k
-    assert np.abs(got["Jp"] - ref["Jp"]).max() <= 1e-4 * k
+    noise = 0.0
+    if res >= 256 and model is not None:
+        e = {co.SNOW: float(np.exp(10.0 * (1.0 - float(ref["Jp"].min())))), co.JELLY: 0.3, co.LIQUID: 1.0}[model]
+        noise = 8 * float(np.finfo(np.float32).eps) * 1e-4 * (4.0 * res * res) * 2.0 * (1e4 / 2.4) * e / res
+    assert np.abs(got["x"] - ref["x"]).max() <= (2.4e-7 + 1e-4 * noise) * k
+    assert np.abs(got["v"] - ref["v"]).max() <= (1e-5 * vmax + noise) * k
+    assert np.abs(got["F"] - ref["F"]).max() <= (2e-5 + 1e-4 * 4 * res * noise) * k
+    assert np.abs(got["C"] - ref["C"]).max() <= (5e-5 * cmax + 1e-6 * 4 * res * vmax + 4 * res * noise) * k
+    assert np.abs(got["Jp"] - ref["Jp"]).max() <= (1e-4 + 1e-4 * 4 * res * noise) * k
 
 
 @pytest.mark.parametrize("sort_every", [1, 3])
@@ -91,7 +97,7 @@ def test_two_logical_slabs_on_one_gpu(dim, model, sort_every):
     assert (seen == 1).all()
     ref = co.CpuSim(x, model, res, v=v)
     ref.advance(steps)
-    check(got, ref.particles(), steps, res)
+    check(got, ref.particles(), steps, res, model)
     # and the single-domain CUDA path agrees too
     one = nm.MPMSimulation(x, model, res, v=v)
     one.advance(steps)
@@ -104,6 +110,15 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def thin_block_512():
+    """cfg4-shaped: res 512, 8 particles per cell, a block only 24 cells thick along x — with 8 ranks the slabs hit
+    the minimum width, some ranks start (almost) empty, and every particle is within a few cells of a slab cut."""
+    x = nm.cube(3, 48, 0.25, 0.25 + 47 * (0.25 / 255))
+    v = np.zeros_like(x)
+    v[:, 0] = 12.0   # 0.6 cells per step at res 512: particles cross a cut every other step
+    return x, v
+
+
 def _nccl_worker(rank, world, port, dim, model, res, steps, rebalance, native, q):
     import torch
     import torch.distributed as dist
@@ -111,7 +126,7 @@ def _nccl_worker(rank, world, port, dim, model, res, steps, rebalance, native, q
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        x, v = moving_block(dim, res)
+        x, v = thin_block_512() if res == 512 else moving_block(dim, res)
         sim = slab.SlabSimulation(x, model, res, device=rank, rebalance_every=rebalance, native=native, v=v)
         sim.advance(steps)
         out = sim.particles(dst=0)
@@ -121,17 +136,18 @@ def _nccl_worker(rank, world, port, dim, model, res, steps, rebalance, native, q
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dim,model,rebalance,native", [(3, co.JELLY, 0, True), (3, co.SNOW, 2, True), (2, co.LIQUID, 3, True),
-                                                        (3, co.JELLY, 2, False), (2, co.SNOW, 0, False)])
-def test_slab_simulation_over_nccl(dim, model, rebalance, native):
-    """native=True: the protocol inside libnmpm (ncclSend/ncclRecv from C++); False: slab.py over torch.distributed."""
+@pytest.mark.parametrize("dim,model,rebalance,native,res", [
+    (3, co.JELLY, 0, True, 32), (3, co.SNOW, 2, True, 32), (2, co.LIQUID, 3, True, 64), (3, co.JELLY, 2, False, 32),
+    (2, co.SNOW, 0, False, 64), (3, co.JELLY, 3, True, 512), (3, co.SNOW, 0, True, 512)])
+def test_slab_simulation_over_nccl(dim, model, rebalance, native, res):
+    """native=True: the device-driven protocol inside libnmpm (NCCL from C++); False: slab.py over torch.distributed.
+    Every GPU of the box takes part (up to 8); res 512 = the cfg4-shaped thin-slab case."""
     import torch
     import torch.multiprocessing as mp
-    world = min(torch.cuda.device_count(), 4)
+    world = min(torch.cuda.device_count(), 8)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
-    res = 64 if dim == 2 else 32
-    steps = 10 if dim == 2 else (3 if model == co.SNOW else 6)
+    steps = 10 if dim == 2 else (3 if model == co.SNOW else (12 if res == 512 else 6))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -143,7 +159,7 @@ def test_slab_simulation_over_nccl(dim, model, rebalance, native):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert migrated > 0
-    x, v = moving_block(dim, res)
+    x, v = thin_block_512() if res == 512 else moving_block(dim, res)
     ref = co.CpuSim(x, model, res, v=v)
     ref.advance(steps)
-    check(got, ref.particles(), steps, res)
+    check(got, ref.particles(), steps, res, model)
