@@ -191,6 +191,9 @@ int nmpm_slab_histogram(nmpm_handle h, int *d_hist);
 int nmpm_nccl_unique_id(void *out128, const char *libnccl_path);
 int nmpm_slab_comm_init(nmpm_handle h, const void *unique_id128, int rank, int world, const int *bounds,
                         size_t cap_records, const char *libnccl_path);
+/* particle count of the global simulation, the same on every rank (sizes the fixed-capacity migrant messages);
+ * call right after nmpm_slab_comm_init */
+int nmpm_slab_set_global_count(nmpm_handle h, size_t n_global);
 int nmpm_slab_step(nmpm_handle h, int nsteps);
 int nmpm_slab_set_bounds(nmpm_handle h, const int *bounds);
 long long nmpm_slab_migrated(nmpm_handle h);

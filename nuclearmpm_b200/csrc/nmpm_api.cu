@@ -635,6 +635,9 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
         h->n_store = 0;
         h->box_cur = (h->box_cur + 1) % kBoxRing;
         k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + h->box_cur);
+        // an empty slab: its key array is all "gone" marks, and stays aligned with the slots as particles arrive —
+        // no key pass may ever run over the (uninitialised) store
+        if (h->slab) h->keys_valid = true;
         return NMPM_OK;
     }
     const uint32_t n = (uint32_t) h->n;

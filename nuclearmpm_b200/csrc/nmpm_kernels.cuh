@@ -788,18 +788,24 @@ __global__ void __launch_bounds__(256) k_unpack_records(const float* __restrict_
 // box for the coming step, [7] the sender's step number.
 constexpr int kHdrInts = 8;
 
-// after G2P: headers of the two outgoing messages, gone count
+// after G2P: headers of the two outgoing messages, gone count, read-back record.  The header pointers address the
+// NEIGHBOURS' inboxes (peer memory over NVLink, or local send buffers on the NCCL path); `flag_*` (nullable) are the
+// neighbours' arrival flags: the records were written by the G2P kernel before this one in stream order, the header by
+// this thread, then a system-scope fence, then the flag — a neighbour that sees the flag sees all of it.
 template <int D>
-__global__ void k_slab_headers(const int* __restrict__ counts /* n_left, n_right, n_kept, overflow */, const GridBox* __restrict__ box,
-                               int* __restrict__ hdr_left, int* __restrict__ hdr_right, int* __restrict__ ctr, int step,
-                               int* __restrict__ ring) {
+__global__ void k_slab_post(const int* __restrict__ counts /* n_left, n_right, n_kept, overflow */, const GridBox* __restrict__ box,
+                            int* hdr_left, int* hdr_right, int* __restrict__ ctr, int step, int* __restrict__ ring,
+                            int slot_bound, int* flag_left, int* flag_right) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int nl = counts[0], nr = counts[1];
+    if (ctr[0] > slot_bound) ctr[2] |= 8;  // this step's launches did not cover every slot in use
     int* h[2] = {hdr_left, hdr_right};
     for (int s = 0; s < 2; ++s) {
-        h[s][0] = s ? nr : nl;
-        for (int d = 0; d < 3; ++d) h[s][1 + d] = box->lo[d], h[s][4 + d] = box->hi[d];
-        h[s][7] = step;
+        if (!h[s]) continue;
+        volatile int* hv = h[s];
+        hv[0] = s ? nr : nl;
+        for (int d = 0; d < 3; ++d) hv[1 + d] = box->lo[d], hv[4 + d] = box->hi[d];
+        hv[7] = step;
     }
     ctr[1] += nl + nr;
     if (counts[3]) ctr[2] |= 2;  // a send buffer overflowed
@@ -807,20 +813,54 @@ __global__ void k_slab_headers(const int* __restrict__ counts /* n_left, n_right
     for (int k = 0; k < 4; ++k) ring[k] = counts[k];
     for (int d = 0; d < 3; ++d) ring[4 + d] = box->lo[d], ring[7 + d] = box->hi[d];
     ring[10] = step, ring[11] = 0;
+    if (flag_left || flag_right) {
+        __threadfence_system();
+        if (flag_left) *((volatile int*) flag_left) = step;
+        if (flag_right) *((volatile int*) flag_right) = step;
+    }
+}
+
+// receiving side of the peer-memory path: wait until both neighbours have posted step `step` into this rank's inboxes.
+// Bounded: a neighbour that never arrives (it died) must not hang the device — the header count is zeroed, the error
+// bit set, and the host raises the error when it reads the record.
+__global__ void k_slab_wait(const int* flag_from_left, const int* flag_from_right, int step, int* hdr_from_left,
+                            int* hdr_from_right, int* __restrict__ ctr) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int* f[2] = {flag_from_left, flag_from_right};
+    int* hd[2] = {hdr_from_left, hdr_from_right};
+    const long long t0 = clock64();
+    for (int s = 0; s < 2; ++s) {
+        if (!f[s]) continue;
+        bool ok = false;
+        while (true) {
+            int v;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f[s]) : "memory");
+            if (v >= step) {
+                ok = true;
+                break;
+            }
+            if (clock64() - t0 > 20000000000LL) break;  // ~10 s at 2 GHz
+            __nanosleep(200);
+        }
+        if (!ok) {
+            hd[s][0] = 0;
+            atomicOr(ctr + 2, 4);
+        }
+    }
+    __threadfence_system();
 }
 
 // receiving side: append the records of both neighbours behind slot ctr[0] and bin them; counts come from the headers
 template <int D>
-__global__ void __launch_bounds__(256) k_unpack_records2(const float* __restrict__ rec_left, const float* __restrict__ rec_right,
+__global__ void __launch_bounds__(256) k_unpack_records2(const float* rec_left, const float* rec_right,
                                                          uint32_t cap_msg_left, uint32_t cap_msg_right, uint32_t cap_store,
                                                          ParticleStore T, MaterialParams P, int tiles_per_axis,
                                                          uint32_t* __restrict__ keys, GridBox* __restrict__ box, int* __restrict__ ctr) {
-    constexpr int W = RecordTraits<D>::WORDS;
-    const uint32_t cl = rec_left ? min((uint32_t) __float_as_int(__ldg(rec_left)), cap_msg_left) : 0u;
-    const uint32_t cr = rec_right ? min((uint32_t) __float_as_int(__ldg(rec_right)), cap_msg_right) : 0u;
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= cl + cr) return;
+    constexpr int W = RecordTraits<D>::WORDS;  // (rec_*: no __restrict__/__ldg — written by another GPU during this launch's lifetime)
+    const uint32_t cl = rec_left ? min((uint32_t) __float_as_int(rec_left[0]), cap_msg_left) : 0u;
+    const uint32_t cr = rec_right ? min((uint32_t) __float_as_int(rec_right[0]), cap_msg_right) : 0u;
     const uint32_t first = (uint32_t) ctr[0];  // not modified by this kernel (k_ctr_after_unpack follows)
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cl + cr; j += gridDim.x * blockDim.x) {
     const uint32_t i = first + j;
     if (i >= cap_store) {
         atomicOr(ctr + 2, 1);
@@ -848,9 +888,10 @@ __global__ void __launch_bounds__(256) k_unpack_records2(const float* __restrict
 #pragma unroll
     for (int d = 0; d < D; ++d) b[d] = min(max(b[d], 0), P.res - 2);
     box_update<D>(box, b, true);
+    }
 }
 
-__global__ void k_ctr_after_unpack(const float* __restrict__ rec_left, const float* __restrict__ rec_right, uint32_t cap_msg_left,
+__global__ void k_ctr_after_unpack(const float* rec_left, const float* rec_right, uint32_t cap_msg_left,
                                    uint32_t cap_msg_right, uint32_t cap_store, int* __restrict__ ctr, int* __restrict__ ring) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const uint32_t cl = rec_left ? min((uint32_t) __float_as_int(rec_left[0]), cap_msg_left) : 0u;

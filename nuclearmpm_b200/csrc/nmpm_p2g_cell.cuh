@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(kP2GWarps * 32, kP2GColsMinB) k_p2g_cols(Parti
     // ---- phase A (lane = particle) ----------------------------------------------------------
     // slab mode: a slot whose particle migrated away (or that was never filled) leaves an all-zero packet with node -1
     const bool gone = lane < cnt && gone_keys && __ldg(gone_keys + first + lane) == kKeyGone;
+    if (gone_keys && !__any_sync(0xffffffffu, lane < cnt && !gone)) return;  // nothing to scatter in this warp
     if (gone) {
         float4* my = &pkt[warp][lane * CH];
 #pragma unroll
@@ -412,6 +413,18 @@ __global__ void __launch_bounds__(kP2GWarps * 32, MINB) k_p2g_streams(ParticleSt
     }
 
     for (int c = 0; c < chunks; ++c) {
+        // slab mode: the slots beyond the slab's particle count are all marked gone — nothing to scatter in such a chunk
+        if (gone_keys && !__any_sync(0xffffffffu, have && !gone)) {
+            const int pos = (c + 1) * wa + ia;
+            have = (c + 1 < chunks) && pos < len_a;
+            gone = false;
+            if (have) {
+                slot = first + (uint32_t) (off_a + pos);
+                gone = __ldg(gone_keys + slot) == kKeyGone;
+                if (!gone) p2g_load_raw(S, perm ? __ldg(perm + slot) : slot, raw);
+            }
+            continue;
+        }
         // ---- phase A (lane = particle of stream ga) ------------------------------------------
         if (have && gone) {
             float4* my = &pkt[warp][lane * CH];

@@ -15,7 +15,7 @@
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef enum { ncclSuccess = 0 } ncclResult_t;
-typedef enum { ncclInt32 = 2, ncclFloat32 = 7 } ncclDataType_t;
+typedef enum { ncclInt8 = 0, ncclInt32 = 2, ncclFloat32 = 7 } ncclDataType_t;
 #endif
 
 namespace {
@@ -90,15 +90,23 @@ struct nmpm_slab_comm {
     int rank = 0, world = 1;
     std::vector<int> bounds;       // ownership boundaries (world+1), as set by the caller
     std::vector<int> grid_bounds;  // boundaries the particles currently obey (lag one G2P behind `bounds`)
-    size_t cap_records = 0, rec_words = 0, plane_nodes = 0;
+    size_t cap_records = 0, rec_words = 0, plane_nodes = 0, n_global = 0;
     float4 *pl_send[2] = {nullptr, nullptr}, *pl_recv[2] = {nullptr, nullptr};  // [0] = left, [1] = right neighbour
-    float *mig_send[2] = {nullptr, nullptr}, *mig_recv[2] = {nullptr, nullptr};  // (1 + cap_records) records each
+    // Migrants travel through peer memory (CUDA IPC over NVLink): `inbox` holds this rank's four receive buffers
+    // [from side 0/1][step parity], (1 + cap_records) records each; G2P writes the records of a leaving particle straight
+    // into the NEIGHBOUR's inbox, k_slab_post adds header + arrival flag, k_slab_wait on the other side waits for it.
+    // No message size has to be agreed and only the bytes of actual migrants cross the link.
+    float* inbox = nullptr;
+    int* flags = nullptr;                          // [0] posted by the left neighbour, [1] by the right one
+    float* peer_inbox[2] = {nullptr, nullptr};     // the left / right neighbour's `inbox`
+    int* peer_flags[2] = {nullptr, nullptr};
+    float* dummy = nullptr;                        // record sink for a side without neighbour (capacity 0)
+    size_t inbox_stride = 0;                       // floats per receive buffer
     int *d_mine = nullptr, *d_ring = nullptr, *h_ring = nullptr;
     cudaEvent_t ev_ring[kRing] = {};
     long long step_no = 0;          // steps issued through nmpm_slab_step
     long long bounds_step = -1000;  // step at which the ownership boundaries last changed
-    size_t k_hist[kRing] = {};      // records received at most in step s (sum of both message capacities)
-    long long migrated = 0;
+    long long migrated = 0, acct_step = 0;  // records of steps < acct_step are in `migrated`
     // NMPM_SLAB_TRACE=1: device time of the segments of a free-running step (events, one sync per nmpm_slab_step call)
     bool trace = false;
     std::vector<cudaEvent_t> tev;  // 5 per step: start, after P2G, after plane exchange, after G2P, after migrants
@@ -119,9 +127,13 @@ struct nmpm_slab_comm {
 static void slab_comm_free(nmpm_sim* h) {
     nmpm_slab_comm* c = h->sc;
     if (!c) return;
+    cudaStreamSynchronize(h->stream);
     for (int s = 0; s < 2; ++s) {
-        cudaFree(c->pl_send[s]), cudaFree(c->pl_recv[s]), cudaFree(c->mig_send[s]), cudaFree(c->mig_recv[s]);
+        cudaFree(c->pl_send[s]), cudaFree(c->pl_recv[s]);
+        if (c->peer_inbox[s]) cudaIpcCloseMemHandle(c->peer_inbox[s]);
+        if (c->peer_flags[s]) cudaIpcCloseMemHandle(c->peer_flags[s]);
     }
+    cudaFree(c->inbox), cudaFree(c->flags), cudaFree(c->dummy);
     cudaFree(c->d_mine), cudaFree(c->d_ring);
     for (cudaEvent_t e : c->ev_ring)
         if (e) cudaEventDestroy(e);
@@ -210,17 +222,6 @@ static int slab_exchange_planes(nmpm_sim* h, const int* rec) {
     return NMPM_OK;
 }
 
-// capacity (records) of the migrant message exchanged with neighbour `side` in the coming step
-static size_t slab_message_capacity(const nmpm_sim* h, const int* rec, int side) {
-    const nmpm_slab_comm* c = h->sc;
-    const bool has = side ? c->rank < c->world - 1 : c->rank > 0;
-    if (!has) return 0;
-    // no record yet, or the boundaries moved within the last few steps (whole planes of particles change owner at once)
-    if (!rec || c->step_no - c->bounds_step < 2 * kLag + 2) return c->cap_records;
-    const size_t sent = (size_t) rec[side], got = (size_t) rec[12 + 8 * side];
-    return std::min(c->cap_records, 2 * std::max(sent, got) + 16384);
-}
-
 // the step's G2P half with per-side send capacities (nmpm_slab_grid_g2p is the public single-capacity form)
 static int slab_grid_g2p2(nmpm_sim* h, float* send_left, size_t cap_left, float* send_right, size_t cap_right, int* d_counts) {
     if (h->phase_next != 1) {
@@ -290,14 +291,38 @@ int nmpm_slab_comm_init(nmpm_handle h, const void* unique_id128, int rank, int w
     ncclUniqueId id;
     std::memcpy(&id, unique_id128, sizeof(id));
     NCCL_TRY(h, g_nccl.CommInitRank(&c->comm, world, id, rank));
-    const size_t msg_bytes = (1 + cap_records) * c->rec_words * sizeof(float);
     for (int s = 0; s < 2; ++s) {
         CUDA_TRY(h, cudaMalloc(&c->pl_send[s], 2 * c->plane_nodes * sizeof(float4)));
         CUDA_TRY(h, cudaMalloc(&c->pl_recv[s], 2 * c->plane_nodes * sizeof(float4)));
-        CUDA_TRY(h, cudaMalloc(&c->mig_send[s], msg_bytes));
-        CUDA_TRY(h, cudaMalloc(&c->mig_recv[s], msg_bytes));
-        CUDA_TRY(h, cudaMemset(c->mig_send[s], 0, c->rec_words * sizeof(float)));
-        CUDA_TRY(h, cudaMemset(c->mig_recv[s], 0, c->rec_words * sizeof(float)));
+    }
+    c->inbox_stride = (1 + cap_records) * c->rec_words;
+    CUDA_TRY(h, cudaMalloc(&c->inbox, 4 * c->inbox_stride * sizeof(float)));
+    CUDA_TRY(h, cudaMemset(c->inbox, 0, 4 * c->inbox_stride * sizeof(float)));
+    CUDA_TRY(h, cudaMalloc(&c->flags, 64));
+    CUDA_TRY(h, cudaMemset(c->flags, 0, 64));
+    CUDA_TRY(h, cudaMalloc(&c->dummy, 2 * c->rec_words * sizeof(float)));
+    CUDA_TRY(h, cudaMemset(c->dummy, 0, 2 * c->rec_words * sizeof(float)));
+    {   // exchange the IPC handles of inbox + flags (one all-gather at set-up), open the two neighbours'
+        struct Handles {
+            cudaIpcMemHandle_t inbox, flags;
+        } mine_h;
+        CUDA_TRY(h, cudaIpcGetMemHandle(&mine_h.inbox, c->inbox));
+        CUDA_TRY(h, cudaIpcGetMemHandle(&mine_h.flags, c->flags));
+        char *d_in = nullptr, *d_all = nullptr;
+        CUDA_TRY(h, cudaMalloc(&d_in, sizeof(Handles)));
+        CUDA_TRY(h, cudaMalloc(&d_all, (size_t) world * sizeof(Handles)));
+        CUDA_TRY(h, cudaMemcpyAsync(d_in, &mine_h, sizeof(Handles), cudaMemcpyHostToDevice, h->stream));
+        NCCL_TRY(h, g_nccl.AllGather(d_in, d_all, sizeof(Handles), ncclInt8, c->comm, h->stream));
+        std::vector<Handles> all((size_t) world);
+        CUDA_TRY(h, cudaMemcpyAsync(all.data(), d_all, (size_t) world * sizeof(Handles), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(d_in), cudaFree(d_all);
+        for (int sd = 0; sd < 2; ++sd) {
+            const int nb = sd ? rank + 1 : rank - 1;
+            if (nb < 0 || nb >= world) continue;
+            CUDA_TRY(h, cudaIpcOpenMemHandle((void**) &c->peer_inbox[sd], all[(size_t) nb].inbox, cudaIpcMemLazyEnablePeerAccess));
+            CUDA_TRY(h, cudaIpcOpenMemHandle((void**) &c->peer_flags[sd], all[(size_t) nb].flags, cudaIpcMemLazyEnablePeerAccess));
+        }
     }
     CUDA_TRY(h, cudaMalloc(&c->d_mine, 12 * sizeof(int)));
     CUDA_TRY(h, cudaMemset(c->d_mine, 0, 12 * sizeof(int)));
@@ -307,6 +332,7 @@ int nmpm_slab_comm_init(nmpm_handle h, const void* unique_id128, int rank, int w
     std::memset(c->h_ring, 0, (size_t) kRing * kRingInts * sizeof(int));
     for (cudaEvent_t& e : c->ev_ring) CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     h->dev_counts = true;
+    c->n_global = (size_t) world * h->n;  // estimate until nmpm_slab_set_global_count is called
     const char* tr = std::getenv("NMPM_SLAB_TRACE");
     c->trace = tr && *tr && *tr != '0';
     return NMPM_OK;
@@ -323,7 +349,18 @@ int nmpm_slab_set_bounds(nmpm_handle h, const int* bounds) {
     return nmpm_slab_set_range(h, x0, x1);
 }
 
-long long nmpm_slab_migrated(nmpm_handle h) { return (h && h->sc) ? h->sc->migrated : 0; }
+// records sent so far (synchronises the stream: the step only accounts records that are two steps old)
+long long nmpm_slab_migrated(nmpm_handle h) {
+    if (!h || !h->sc) return 0;
+    nmpm_slab_comm* c = h->sc;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (; c->acct_step < c->step_no; ++c->acct_step) {
+        const int* r2 = slab_record(h, c->acct_step);
+        if (r2) c->migrated += (long long) r2[0] + r2[1];
+    }
+    return c->migrated;
+}
 
 int nmpm_slab_step(nmpm_handle h, int nsteps) {
     if (int rc = slab_check(h, "nmpm_slab_step")) return rc;
@@ -358,60 +395,86 @@ int nmpm_slab_step(nmpm_handle h, int nsteps) {
                 return NMPM_ERR_INVALID;
             }
             if ((rec[28 + 2] & 2) || rec[3]) {
-                h->last_error = "slab step: migration send buffer overflow (raise cap_records)";
+                h->last_error = "slab step: migration buffer overflow (raise cap_records), or a particle left the outermost slab";
                 return NMPM_ERR_INVALID;
+            }
+            if (rec[28 + 2] & 8) {
+                h->last_error = "slab step: more slots in use than the launches covered (particle burst beyond the growth bound)";
+                return NMPM_ERR_INVALID;
+            }
+            if (rec[28 + 2] & 4) {
+                h->last_error = "slab step: a neighbour never posted its migrants (peer flag wait timed out)";
+                return NMPM_ERR_CUDA;
             }
             if ((!has[0] && rec[0]) || (!has[1] && rec[1])) {
                 h->last_error = "a particle left the outermost slab";
                 return NMPM_ERR_INVALID;
             }
-            c->migrated += (long long) rec[0] + rec[1];
-            // slots in use: true count after step e, plus whatever the unpacks since then may have appended
-            size_t bound = (size_t) rec[28];
-            for (long long k = e + 1; k < c->step_no; ++k) bound += c->k_hist[k % kRing];
-            h->n_store = std::min(h->cap, std::max(bound, (size_t) 1));
+            for (; c->acct_step <= e; ++c->acct_step) {
+                const int* r2 = slab_record(h, c->acct_step);
+                if (r2) c->migrated += (long long) r2[0] + r2[1];
+            }
         }
-        const size_t K[2] = {slab_message_capacity(h, rec, 0), slab_message_capacity(h, rec, 1)};
+        // Slots the launches of this step cover.  The host does not know how many are in use: the true count of two steps
+        // ago plus generous growth (one unpack has happened since: two sides, each at most a few times what arrived then,
+        // or 3 % of the store when a burst starts from nothing), capped by the allocation.  k_slab_post verifies the bound
+        // on the device (error bit 8).  Slots beyond the true count carry kKeyGone and are skipped, so a loose bound only
+        // costs empty warps and sort keys.
+        if (c->step_no >= 1) {
+            size_t bound = h->cap;
+            if (rec) {
+                const size_t n_true = (size_t) rec[28], arrived = (size_t) std::max(rec[12], rec[20]);
+                const size_t growth = std::max(4 * arrived, n_true / 32) + 16384;
+                bound = std::min(h->cap, n_true + 3 * growth);
+            }
+            h->n_store = bound;
+        }
         const bool stable = c->step_no - c->bounds_step >= 2 * kLag + 2;
+        const int step_tag = (int) c->step_no + 1;                 // what the flags carry (0 = nothing posted yet)
+        const size_t par = (size_t) (c->step_no & 1);
+        // where this step's migrants go: the neighbours' inboxes [their side facing me][parity]; none: a sink of capacity 0
+        float* out[2];
+        size_t K[2];
+        for (int sd = 0; sd < 2; ++sd) {
+            out[sd] = has[sd] ? c->peer_inbox[sd] + ((size_t) (1 - sd) * 2 + par) * c->inbox_stride : c->dummy;
+            K[sd] = has[sd] ? c->cap_records : 0;
+        }
+        const float* in[2] = {has[0] ? c->inbox + (0 * 2 + par) * c->inbox_stride : nullptr,
+                              has[1] ? c->inbox + (1 * 2 + par) * c->inbox_stride : nullptr};
 
         mark(s, 0);
         if (int rc = nmpm_slab_p2g(h)) return rc;
         mark(s, 1);
         if (int rc = slab_exchange_planes(h, stable ? rec : nullptr)) return rc;
         mark(s, 2);
-        if (int rc = slab_grid_g2p2(h, c->mig_send[0] + W, K[0], c->mig_send[1] + W, K[1], c->d_mine)) return rc;
+        if (int rc = slab_grid_g2p2(h, out[0] + W, K[0], out[1] + W, K[1], c->d_mine)) return rc;
         c->grid_bounds = c->bounds;  // after this G2P every particle obeys the current boundaries
         mark(s, 3);
-        // ---- migrants: headers, one NCCL group, append behind the device-side slot counter ------------------------------
-        NMPM_DISPATCH_DIM(h, (k_slab_headers<D><<<1, 32, 0, h->stream>>>(c->d_mine, h->d_box + h->box_cur, (int*) c->mig_send[0],
-                                                                        (int*) c->mig_send[1], h->d_ctr, (int) c->step_no,
-                                                                        c->d_ring)));
-        h->launches++;
+        // ---- migrants: header + flag into the neighbours' inboxes, wait for theirs, append behind the device-side counter ----
+        NMPM_DISPATCH_DIM(h, (k_slab_post<D><<<1, 32, 0, h->stream>>>(c->d_mine, h->d_box + h->box_cur, has[0] ? (int*) out[0] : nullptr,
+                                                                     has[1] ? (int*) out[1] : nullptr, h->d_ctr, step_tag, c->d_ring,
+                                                                     (int) std::min(h->n_store, (size_t) 0x7fffffff),
+                                                                     has[0] ? c->peer_flags[0] + 1 : nullptr,
+                                                                     has[1] ? c->peer_flags[1] + 0 : nullptr)));
+        k_slab_wait<<<1, 32, 0, h->stream>>>(has[0] ? c->flags + 0 : nullptr, has[1] ? c->flags + 1 : nullptr, step_tag,
+                                             (int*) in[0], (int*) in[1], h->d_ctr);
+        h->launches += 2;
         if (has[0] || has[1]) {
-            NCCL_TRY(h, g_nccl.GroupStart());
-            for (int sd = 0; sd < 2; ++sd) {
-                if (!has[sd]) continue;
-                const int nbr = sd ? c->rank + 1 : c->rank - 1;
-                NCCL_TRY(h, g_nccl.Send(c->mig_send[sd], (1 + K[sd]) * W, ncclFloat32, nbr, c->comm, h->stream));
-                NCCL_TRY(h, g_nccl.Recv(c->mig_recv[sd], (1 + K[sd]) * W, ncclFloat32, nbr, c->comm, h->stream));
-            }
-            NCCL_TRY(h, g_nccl.GroupEnd());
-        }
-        const float* rl = has[0] ? c->mig_recv[0] : nullptr;
-        const float* rr = has[1] ? c->mig_recv[1] : nullptr;
-        if (K[0] + K[1]) {
-            NMPM_DISPATCH_DIM(h, (k_unpack_records2<D><<<blocks_for(K[0] + K[1], 256), 256, 0, h->stream>>>(
-                                     rl, rr, (uint32_t) K[0], (uint32_t) K[1], (uint32_t) h->cap, h->store[h->cur], h->P,
-                                     h->tiles_per_axis, h->sort.keys_a, h->d_box + h->box_cur, h->d_ctr)));
+            // launch size: the two-step-old counts with head-room; the kernel strides, so any count is handled
+            size_t guess = 65536;
+            if (rec) guess = 2 * (size_t) std::max(rec[12], rec[20]) + 2 * (size_t) std::max(rec[0], rec[1]) + 65536;
+            guess = std::min(guess, 2 * c->cap_records);
+            NMPM_DISPATCH_DIM(h, (k_unpack_records2<D><<<blocks_for(guess, 256), 256, 0, h->stream>>>(
+                                     in[0], in[1], (uint32_t) c->cap_records, (uint32_t) c->cap_records, (uint32_t) h->cap,
+                                     h->store[h->cur], h->P, h->tiles_per_axis, h->sort.keys_a, h->d_box + h->box_cur, h->d_ctr)));
             h->launches++;
         }
-        k_ctr_after_unpack<<<1, 32, 0, h->stream>>>(rl, rr, (uint32_t) K[0], (uint32_t) K[1], (uint32_t) h->cap, h->d_ctr, c->d_ring);
+        k_ctr_after_unpack<<<1, 32, 0, h->stream>>>(in[0], in[1], (uint32_t) c->cap_records, (uint32_t) c->cap_records,
+                                                    (uint32_t) h->cap, h->d_ctr, c->d_ring);
         h->launches++;
         CUDA_TRY(h, cudaMemcpyAsync(c->h_ring + (size_t) (c->step_no % kRing) * kRingInts, c->d_ring, kRingInts * sizeof(int),
                                     cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaEventRecord(c->ev_ring[c->step_no % kRing], h->stream));
-        c->k_hist[c->step_no % kRing] = K[0] + K[1];
-        h->n_store = std::min(h->cap, h->n_store + K[0] + K[1]);
         ++c->step_no;
         mark(s, 4);
         CUDA_TRY(h, cudaGetLastError());
@@ -439,6 +502,14 @@ int nmpm_slab_step(nmpm_handle h, int nsteps) {
     return NMPM_OK;
 }
 
+// particle count of the whole (global) simulation: every rank must pass the same number (it sizes the migrant messages)
+int nmpm_slab_set_global_count(nmpm_handle h, size_t n_global) {
+    if (int rc = slab_check(h, "nmpm_slab_set_global_count")) return rc;
+    if (!h->sc) return NMPM_ERR_INVALID;
+    h->sc->n_global = n_global;
+    return NMPM_OK;
+}
+
 // true particle / slot counts of a device-driven slab (synchronises the stream)
 int nmpm_slab_counts(nmpm_handle h, long long* particles, long long* slots_in_use) {
     if (int rc = slab_check(h, "nmpm_slab_counts")) return rc;
@@ -449,6 +520,14 @@ int nmpm_slab_counts(nmpm_handle h, long long* particles, long long* slots_in_us
         CUDA_TRY(h, cudaMemcpyAsync(ctr, h->d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         np = (long long) ctr[0] - ctr[1], ns = ctr[0];
+        if (ctr[2]) {  // the step itself reports these two steps late
+            h->last_error = std::string("slab step error bits ") + std::to_string(ctr[2]) +
+                            " (1: particle capacity exceeded, 2: migration buffer overflow / particle left the outermost slab, "
+                            "4: peer flag wait timed out, 8: slot bound exceeded)";
+            if (particles) *particles = np;
+            if (slots_in_use) *slots_in_use = ns;
+            return NMPM_ERR_INVALID;
+        }
     }
     if (particles) *particles = np;
     if (slots_in_use) *slots_in_use = ns;

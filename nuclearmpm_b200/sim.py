@@ -112,6 +112,7 @@ def load_library():
     sig("nmpm_nccl_unique_id", ci, [vp, ct.c_char_p])
     sig("nmpm_slab_comm_init", ci, [vp, vp, ci, ci, _i32p, sz, ct.c_char_p])
     sig("nmpm_slab_step", ci, [vp, ci])
+    sig("nmpm_slab_set_global_count", ci, [vp, sz])
     sig("nmpm_slab_set_bounds", ci, [vp, _i32p])
     sig("nmpm_slab_migrated", ct.c_longlong, [vp])
     sig("nmpm_slab_counts", ci, [vp, ct.POINTER(ct.c_longlong), ct.POINTER(ct.c_longlong)])

@@ -145,7 +145,7 @@ class GpuSlabEngine:
         except Exception:
             return b""
 
-    def native_init(self, dist, group, rank, world, bounds, cap_records):
+    def native_init(self, dist, group, rank, world, bounds, cap_records, n_global=None):
         """Create the library's NCCL communicator: rank 0 makes the unique id, torch.distributed carries it."""
         torch = self.torch
         buf = (ct.c_ubyte * 128)()
@@ -158,6 +158,8 @@ class GpuSlabEngine:
         b = np.ascontiguousarray(bounds, np.int32)
         self.sim._check(self._L.nmpm_slab_comm_init(self._h, raw, rank, world, b.ctypes.data_as(_sim._i32p),
                                                     int(cap_records), path), "nmpm_slab_comm_init")
+        if n_global is not None:
+            self.sim._check(self._L.nmpm_slab_set_global_count(self._h, int(n_global)), "nmpm_slab_set_global_count")
 
     def native_step(self, nsteps):
         self.sim._check(self._L.nmpm_slab_step(self._h, int(nsteps)), "nmpm_slab_step")
@@ -170,7 +172,10 @@ class GpuSlabEngine:
         return int(self._L.nmpm_slab_migrated(self._h))
 
     def num_particles(self):
-        return self.sim.num_particles()
+        """Live particles on this slab (device-driven native step: synchronises and raises on a latched step error)."""
+        np_, ns_ = ct.c_longlong(), ct.c_longlong()
+        self.sim._check(self._L.nmpm_slab_counts(self._h, ct.byref(np_), ct.byref(ns_)), "nmpm_slab_counts")
+        return int(np_.value)
 
     def download_slots(self, out=None, compact=True):
         return self.sim.particles_slots(out, compact)
@@ -243,7 +248,7 @@ class SlabSimulation:
             native = hasattr(e, "native_init") and dist.get_backend(group) == "nccl"
         self.native = bool(native)
         if self.native:
-            e.native_init(dist, group, self.rank, self.world, self.bounds, self.cap_records)
+            e.native_init(dist, group, self.rank, self.world, self.bounds, self.cap_records, self.n_global)
             return
         self.buf_from_left = e.new_buffer(2 * e.plane_words)
         self.buf_from_right = e.new_buffer(2 * e.plane_words)

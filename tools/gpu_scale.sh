@@ -16,7 +16,7 @@ for n in $ns; do
 import json
 try:
     d=json.loads(open("$out/scale_$n.json").read().strip().splitlines()[-1]); r=d.get("roofline") or {}
-    print("N=$n %.3e p-steps/s  %.3f ms/step"%(d["value"], d["ms_per_step"]), d["config"].get("bounds"), d["config"].get("particles_per_rank_min_max"), "roofline", r.get("kernel"), round(r.get("frac",0),3), "e2e %.3e"%d["e2e"]["value"])
+    print("N=$n %.3e p-steps/s  %.3f ms/step"%(d["value"], d["ms_per_step"]), (d.get("run") or {}).get("bounds"), (d.get("run") or {}).get("particles_per_rank_min_max"), "checks", (d.get("checks") or {}).get("ok"), "verify", d.get("verification"), "roofline", r.get("kernel"), round(r.get("frac",0),3), "e2e %.3e"%d["e2e"]["value"])
     for row in (r.get("phase_ms_per_rank") or []): print("   ", {k:round(v,3) for k,v in row.items()})
 except Exception as e: print("parse failed", e)
 PY
