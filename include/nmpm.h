@@ -60,8 +60,11 @@ typedef struct nmpm_options {
     int capacity;     /* slab mode: particle slots to allocate (>= n; room for migrants). 0 = n */
     int g2p_window;   /* 3D G2P node gather: 0 = auto, 1 = straight from global memory (L1/L2),
                          2 = node window of each 128-particle CTA staged in shared memory by the TMA
-                         (cp.async.bulk.tensor + mbarrier; CTAs whose bounding box exceeds the window fall back to 1).
-                         Env NMPM_G2P_WINDOW=0/1 overrides.  Same results up to nothing: both read the same nodes */
+                         (cp.async.bulk.tensor + mbarrier; CTAs whose bounding box exceeds the window fall back to 1),
+                         3 = 2 in persistent CTAs that request the next chunk's particle rows (cp.async) and node
+                         window while the current chunk computes.  Env NMPM_G2P_WINDOW=0/1/2 (= modes 1/2/3) overrides.
+                         Every mode reads the same nodes (same results).  Measured on cfg4: mode 1 is the fastest
+                          and is what 0 selects */
     int reserved[8];
 } nmpm_options;
 

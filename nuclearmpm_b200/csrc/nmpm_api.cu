@@ -70,6 +70,7 @@ struct nmpm_sim {
     bool local_reorder = true;  // in-place G2P re-groups each warp's 32 slots by cell key (NMPM_LOCAL_REORDER=0: off)
     CUtensorMap grid_map{};     // 3D: the grid as a rank-4 tensor {4 floats, z, y, x} with one x-plane window box (G2P)
     bool g2p_window = false;    // 3D: G2P stages its node window through the TMA (NMPM_G2P_WINDOW=0: off)
+    bool g2p_pipe = false;      // 3D: ... in the persistent software-pipelined kernel (k_g2p_pipe)
     // device-driven slab step (nmpm_slab_comm.inl): the true slot / gone counts live in d_ctr, `n_store` is only an upper
     // bound for launch sizes, every slot beyond the true count (and every migrated-away slot) carries kKeyGone in keys_a
     bool dev_counts = false;
@@ -308,9 +309,11 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
     CUDA_TRY(h, cudaMemset(h->grid, 0, h->cells * sizeof(float4)));  // the only dense clear; afterwards box by box
     if (dim == 3) {
         // auto = global gather: measured on cfg4, the staged window is 5 % slower (profiles/r02c)
-        bool want = h->opt.g2p_window == 2;
-        if (const char* gw = std::getenv("NMPM_G2P_WINDOW")) want = (*gw != '0');
-        h->g2p_window = want && make_grid_map(h) == NMPM_OK;  // no tensor map: plain global gather
+        int mode = h->opt.g2p_window;  // 0 auto, 1 global gather, 2 one-shot window, 3 pipelined window
+        if (const char* gw = std::getenv("NMPM_G2P_WINDOW")) mode = (*gw >= '0' && *gw <= '3') ? (*gw - '0') + 1 : mode;
+        if (mode == 0) mode = 1;
+        h->g2p_window = mode >= 2 && make_grid_map(h) == NMPM_OK;  // no tensor map: plain global gather
+        h->g2p_pipe = h->g2p_window && mode == 3;
     }
     CUDA_TRY(h, cudaMalloc(&h->d_box, kBoxRing * sizeof(GridBox)));
     CUDA_TRY(h, cudaMalloc(&h->d_box_partial, ((h->cap + 127) / 128 * 4 + 4) * 8 * sizeof(int)));
@@ -650,7 +653,19 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
     const uint32_t* gone_keys = (h->dev_counts || (h->slab && !h->perm && h->n_gone)) ? h->sort.keys_a : nullptr;
     const int box_next = (h->box_cur + 1) % kBoxRing;
     k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + box_next);
-    if (h->g2p_window) {  // 3D only (set at creation)
+    if (h->g2p_window && h->g2p_pipe) {  // 3D only: persistent CTAs, pipelined rows (cp.async) and node windows (TMA)
+        const unsigned chunks = blocks_for(n, 128);
+        const unsigned grid_ctas = chunks < (unsigned) (148 * NMPM_G2P_PIPE_MINB) ? chunks : (unsigned) (148 * NMPM_G2P_PIPE_MINB);
+        if (h->model == 0)
+            k_g2p_pipe<0><<<grid_ctas, 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error,
+                                                            mig, h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
+        else if (h->model == 1)
+            k_g2p_pipe<1><<<grid_ctas, 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error,
+                                                            mig, h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
+        else
+            k_g2p_pipe<2><<<grid_ctas, 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error,
+                                                            mig, h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
+    } else if (h->g2p_window) {  // 3D only (set at creation): one-shot CTAs with a TMA-staged node window
         constexpr int D = 3;
         if (h->model == 0)
             k_g2p_gather<D, 0, true><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out,

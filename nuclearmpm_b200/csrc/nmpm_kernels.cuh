@@ -15,6 +15,9 @@
 #ifndef NMPM_P2G_MINB
 #define NMPM_P2G_MINB 8
 #endif
+#ifndef NMPM_G2P_PIPE_MINB
+#define NMPM_G2P_PIPE_MINB 6   // persistent pipelined G2P: 80 registers (the window posting sits in the middle of the live state)
+#endif
 
 namespace nmpm {
 
@@ -105,7 +108,8 @@ __device__ __forceinline__ void box_update(GridBox* __restrict__ box, const int 
 // GridBox cost +40 % G2P time: half a million same-address L2 round trips at the tail of every warp.)
 // `live` = ballot of the lanes that own a particle, taken before any lane left the kernel.
 template <int D>
-__device__ __forceinline__ void box_partial_write(int* __restrict__ partial, unsigned live, const int (&b)[D], bool valid) {
+__device__ __forceinline__ void box_partial_write(int* __restrict__ partial, unsigned live, const int (&b)[D], bool valid,
+                                                  uint32_t warp_slot) {
     __syncwarp(live);
     int mn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, mx[3] = {(int) 0x80000000, (int) 0x80000000, (int) 0x80000000};
 #pragma unroll
@@ -114,7 +118,7 @@ __device__ __forceinline__ void box_partial_write(int* __restrict__ partial, uns
         mx[d] = __reduce_max_sync(live, valid ? b[d] : (int) 0x80000000);
     }
     if ((threadIdx.x & 31) == __ffs(live) - 1) {
-        int4* out = reinterpret_cast<int4*>(partial + (size_t) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8);
+        int4* out = reinterpret_cast<int4*>(partial + (size_t) warp_slot * 8);
         out[0] = make_int4(mn[0], mn[1], mn[2], mx[0]);
         out[1] = make_int4(mx[1], mx[2], 0, 0);
     }
@@ -421,6 +425,13 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
+// 16-byte asynchronous global -> shared copies (LDGSTS), one commit group per thread
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // Node window of the TMA-staged G2P: up to kWinX x-planes of kWinY x kWinZ nodes (float4), one TMA box per plane
 // (tensor-map box {4 floats, kWinZ, kWinY, 1}); planes sit kWinPitch nodes apart (128-byte aligned for the TMA).
 // kWinZ = 13 (odd): rows of a plane start 13 nodes apart, which spreads the 16-byte bank groups of neighbouring rows.
@@ -593,7 +604,7 @@ __device__ __forceinline__ void g2p_finish(PState<D>& p, const Mat<D>& Cn, const
 #pragma unroll
         for (int d = 0; d < D; ++d) b[d] = min(max(b[d], 0), P.res - 2);
         // migrants stay in the sender's box: the box table of the slab protocol must cover them until they are unpacked
-        box_partial_write<D>(box_partial, live, b, true);
+        box_partial_write<D>(box_partial, live, b, true, i >> 5);
     }
 }
 
@@ -746,6 +757,179 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
     }
     g2p_finish<D, MODEL>(p, Cn, vn, S, T, perm, src, i, live, P, keys_out, tiles_per_axis, mig, box_partial, gone_keys,
                          local_reorder);
+}
+
+// ---- K4, software-pipelined (3D): persistent CTAs, asynchronous particle rows and node windows ------------------------
+//
+// The one-shot kernel above starts every CTA with a dependent chain — positions from DRAM, bounding box, node loads —
+// and the 27 node loads of the gather are its long-scoreboard stalls (profiles/r01ze, r02c).  Here a CTA of 128 threads
+// is persistent and walks chunks of 128 slots (chunk = blockIdx.x, += gridDim.x).  While chunk k is computed, everything
+// chunk k+1 needs is already on its way:
+//   [A] the rows q0..q3 of chunk k (x, Jp, F) are read from shared memory into registers; the rows of chunk k+1 are
+//       requested with 16-byte cp.async copies (LDGSTS; through the sort permutation on re-binned steps);
+//   [B] the node window of chunk k has landed (mbarrier, posted one iteration ago): 27-node gather from shared memory;
+//   [C] the rows of k+1 have landed: bounding box of their stencil bases (warp reductions + one shared-memory round),
+//       one elected thread issues one TMA box per x-plane of the window of chunk k+1 (the single window buffer is free:
+//       every warp has passed its gather);
+//   [D] F' = (I + dt C) F, snow projection / liquid reset, next cell key, re-grouping, stores — ~1000 instructions per
+//       warp during which the window of k+1 travels.
+// Chunks whose box exceeds the window (dispersed particles) gather from global memory; shared memory: 8 KB rows +
+// 20 KB window per CTA, 8 CTAs per SM as before.
+template <int MODEL>
+__global__ void __launch_bounds__(128, NMPM_G2P_PIPE_MINB) k_g2p_pipe(ParticleStore S, ParticleStore T, const uint32_t* __restrict__ perm,
+                                                                 uint32_t n, MaterialParams P, const float4* __restrict__ grid,
+                                                                 uint32_t* __restrict__ keys_out, int tiles_per_axis,
+                                                                 int* __restrict__ error_flag, MigrateArgs mig,
+                                                                 int* __restrict__ box_partial, const uint32_t* __restrict__ gone_keys,
+                                                                 int local_reorder, const __grid_constant__ CUtensorMap grid_map) {
+    constexpr int D = 3;
+    __shared__ __align__(128) float4 win[kWinX * kWinPitch];
+    __shared__ __align__(16) float4 rows[4][128];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ int red[4][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nchunks = (n + 127u) >> 7;
+    if (blockIdx.x >= nchunks) return;
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+
+    // request the rows of `chunk` for this thread's slot; returns whether the slot holds a particle of this slab
+    auto request_rows = [&](uint32_t chunk, uint32_t& src_out) -> bool {
+        const uint32_t i = chunk * 128u + threadIdx.x;
+        const bool m = chunk < nchunks && i < n && !(gone_keys && __ldg(gone_keys + i) == kKeyGone);
+        src_out = i;
+        if (m) {
+            const uint32_t src = perm ? __ldg(perm + i) : i;
+            src_out = src;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cp_async16(&rows[k][threadIdx.x], S.q[k] + src);
+        }
+        cp_async_commit();
+        return m;
+    };
+    // bounding box of the CTA's stencil bases -> window origin; the elected thread posts the TMA boxes.  Returns whether
+    // the chunk gathers from the window (CTA-uniform).
+    auto post_window = [&](bool m, const int (&base)[3], int (&origin)[3]) -> bool {
+        int mn[3], mx[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            mn[d] = __reduce_min_sync(0xffffffffu, m ? base[d] : 0x7fffffff);
+            mx[d] = __reduce_max_sync(0xffffffffu, m ? base[d] : (int) 0x80000000);
+        }
+        if (lane == 0) {
+            *reinterpret_cast<int4*>(&red[warp][0]) = make_int4(mn[0], mn[1], mn[2], mx[0]);
+            *reinterpret_cast<int2*>(&red[warp][4]) = make_int2(mx[1], mx[2]);
+        }
+        __syncthreads();  // also: every warp is past its gather from the window, and past reading `red` of the last round
+#pragma unroll
+        for (int wi = 0; wi < 4; ++wi) {
+            const int4 a = *reinterpret_cast<const int4*>(&red[wi][0]);
+            const int2 b = *reinterpret_cast<const int2*>(&red[wi][4]);
+            mn[0] = min(mn[0], a.x), mn[1] = min(mn[1], a.y), mn[2] = min(mn[2], a.z);
+            mx[0] = max(mx[0], a.w), mx[1] = max(mx[1], b.x), mx[2] = max(mx[2], b.y);
+        }
+        const int ex = mx[0] - mn[0] + 3, ey = mx[1] - mn[1] + 3, ez = mx[2] - mn[2] + 3;
+        const bool fits = ex >= 3 && ey >= 3 && ez >= 3 && ex <= kWinX && ey <= kWinY && ez <= kWinZ;
+        if (fits && threadIdx.x == 0) {
+            mbar_arrive_expect_tx(&mbar, (uint32_t) ex * kWinPlaneBytes);
+            for (int px = 0; px < ex; ++px) tma_load_4d(win + px * kWinPitch, &grid_map, &mbar, 0, mn[2], mn[1], mn[0] + px);
+        }
+        origin[0] = mn[0], origin[1] = mn[1], origin[2] = mn[2];
+        __syncthreads();  // `red` may be rewritten by the next round only after everybody has read it
+        return fits;
+    };
+
+    // ---- prologue: rows and window of the first chunk ----------------------------------------------------------
+    uint32_t chunk = blockIdx.x;
+    uint32_t src_next;
+    bool mine_next = request_rows(chunk, src_next);
+    cp_async_wait_all();
+    // stencil base of the staged position (clamped like stencil_of does): all the window origin needs; the full stencil is
+    // recomputed at [A] rather than carried in registers across [D]
+    auto staged_base = [&](bool m, int (&b)[3]) {
+        const float4 a0 = m ? rows[0][threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float xs[3] = {a0.x, a0.y, a0.z};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const Stencil1 st = stencil_axis(xs[d], P.inv_dx, P.res);
+            b[d] = st.ok ? st.base : min(max(st.base, 0), P.res - 2);
+        }
+    };
+    int origin_n[3];
+    bool inwin_next;
+    {
+        int bn[3];
+        staged_base(mine_next, bn);
+        inwin_next = post_window(mine_next, bn, origin_n);
+    }
+    uint32_t parity = 0;
+
+    for (; chunk < nchunks; chunk += gridDim.x) {
+        // ---- [A] this chunk's particle out of the staged rows; next chunk's rows requested --------------------
+        const bool mine = mine_next, in_window = inwin_next;
+        const uint32_t src = src_next, i = chunk * 128u + threadIdx.x;
+        PState<D> p;
+        int base[3] = {0, 0, 0};
+        const int origin[3] = {origin_n[0], origin_n[1], origin_n[2]};
+        float fx[3], w[3][3];
+        if (mine) {
+            const float4 a0 = rows[0][threadIdx.x], a1 = rows[1][threadIdx.x], a2 = rows[2][threadIdx.x], a3 = rows[3][threadIdx.x];
+            p.x[0] = a0.x, p.x[1] = a0.y, p.x[2] = a0.z, p.Jp = a0.w;
+            p.F.m[0] = a1.x, p.F.m[1] = a1.y, p.F.m[2] = a1.z, p.F.m[3] = a1.w;
+            p.F.m[4] = a2.x, p.F.m[5] = a2.y, p.F.m[6] = a2.z, p.F.m[7] = a2.w;
+            p.F.m[8] = a3.x;
+            if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
+        }
+        const unsigned live = __ballot_sync(0xffffffffu, mine);
+        const uint32_t next = chunk + gridDim.x;
+        mine_next = request_rows(next, src_next);  // each thread overwrites only the row slots it has just read
+
+        // ---- [B] gather: from the window once it has landed, else from global memory ---------------------------
+        float vn[3];
+        Mat<3> Cn;
+        const float four_inv_dx = 4.0f * P.inv_dx;
+        bool use_window = in_window;
+        if (in_window) {
+            uint32_t spins = 0;
+            while (!mbar_try_wait(&mbar, parity)) {
+                if (++spins > (1u << 22)) {  // cannot happen short of a bad descriptor: do not hang the device
+                    use_window = false;
+                    atomicOr(error_flag, 4);
+                    break;
+                }
+            }
+            parity ^= 1u;
+        }
+        if (mine) {
+            if (use_window) {
+                const float4* node = win + ((base[0] - origin[0]) * kWinPitch + (base[1] - origin[1]) * kWinZ + (base[2] - origin[2]));
+                g2p_gather3(WindowNodes<kWinPitch, kWinZ>{node}, w, fx, four_inv_dx, vn, Cn);
+            } else {
+                const int n1 = P.n1;
+                const GlobalNodes nodes{grid + ((size_t) (base[0] * n1 + base[1]) * n1 + base[2]), n1 * n1, n1};
+                g2p_gather3(nodes, w, fx, four_inv_dx, vn, Cn);
+            }
+        }
+
+        // ---- [C] next chunk: rows have landed -> stencil, bounding box, window boxes posted -----------------------
+        cp_async_wait_all();
+        {
+            int bn[3];
+            staged_base(mine_next, bn);
+            inwin_next = post_window(mine_next, bn, origin_n);  // (next >= nchunks: nobody is `mine`, nothing is posted)
+        }
+
+        // ---- [D] update, re-binning, stores ---------------------------------------------------------------------------
+        if (live == 0u) {
+            if (lane == 0) {
+                int4* out = reinterpret_cast<int4*>(box_partial + (size_t) (i >> 5) * 8);
+                out[0] = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, (int) 0x80000000);
+                out[1] = make_int4((int) 0x80000000, (int) 0x80000000, 0, 0);
+            }
+        } else if (mine) {
+            g2p_finish<D, MODEL>(p, Cn, vn, S, T, perm, src, i, live, P, keys_out, tiles_per_axis, mig, box_partial, gone_keys,
+                                 local_reorder);
+        }
+    }
 }
 
 // slab migration, receiving side: append records to slots [first, first + count) and bin them

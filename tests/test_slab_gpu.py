@@ -157,6 +157,9 @@ def test_slab_simulation_over_nccl(dim, model, rebalance, native, res):
     # res 512 with the reference's default E / volume = 1 is far beyond the stable time step: perturbations of 1 ulp grow
     # tenfold per step (C at step 4 is off by its own magnitude; single GPU against the oracle just the same) — 3 steps, like 3D snow
     steps = 10 if dim == 2 else (3 if (model == co.SNOW or res == 512) else 6)
+    if res == 512 and model == co.SNOW:
+        steps = 2  # amp ~ 1e5 (tests/test_parity_fullres_gpu.py): a 1e-3 difference in F after step 2 is a clamp-speed
+                   # difference in v at step 3 — free-running 3D snow decorrelates one step earlier than at res 32
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
