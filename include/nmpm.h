@@ -108,6 +108,16 @@ int nmpm_download_grid(nmpm_handle h, float *gv, float *gm, size_t *cells_out);
 /* struct Cell<dim> AoS — src/nclr.h:50-55 (12 B in 2D, 16 B in 3D) */
 int nmpm_download_grid_aos(nmpm_handle h, void *cells_aos, size_t stride, size_t *cells_out);
 
+/* Pipelined host I/O for per-step snapshot loops (the reference's solve_mpm pushes particles() every step,
+ * src/solver.cpp:50-59): both calls only ENQUEUE — the upload's H2D copies run on a copy stream into double-buffered
+ * device staging, the download's D2H copies on another, so the copy-in of step k+1 and the copy-out of step k-1
+ * overlap step k and both PCIe directions stay busy.  Same semantics as the blocking forms below otherwise.  Host
+ * arrays (pinned memory, or the copies serialise) must stay valid/untouched until nmpm_synchronize, or until two
+ * further async calls of the same kind have been issued and completed.  An error is reported by nmpm_synchronize. */
+int nmpm_upload_particles_async(nmpm_handle h, const float *x, const float *v, const float *F, const float *C,
+                                const float *Jp);
+int nmpm_download_particles_async(nmpm_handle h, float *x, float *v, float *F, float *C, float *Jp);
+
 /* Replace the particle state (teacher-forced parity tests / resume from a snapshot: the reference
  * does this by constructing a new sim from a saved particle vector).  n must match.
  * A NULL v / F / C / Jp means "the constructor default" (v = 0, F = diag<dim>(1), C = 0, Jp = 1,

@@ -88,6 +88,17 @@ struct nmpm_sim {
 
     float* staging = nullptr;  // device scratch for import/export
     size_t staging_bytes = 0;
+    // pipelined host I/O (nmpm_upload_particles_async / nmpm_download_particles_async): two copy streams and double-
+    // buffered device staging, so that the H2D copy of step k+1 and the D2H copy of step k-1 overlap step k
+    struct AsyncIo {
+        cudaStream_t s_in = nullptr, s_out = nullptr;
+        float* in[2] = {nullptr, nullptr};
+        float* out[2] = {nullptr, nullptr};
+        size_t bytes = 0;
+        cudaEvent_t in_ready[2] = {}, in_free[2] = {}, out_ready[2] = {}, out_free[2] = {};
+        unsigned k_in = 0, k_out = 0;
+        bool ok = false;
+    } io;
 
     long long steps_done = 0;
     long long launches = 0;
@@ -379,6 +390,15 @@ void nmpm_destroy(nmpm_handle h) {
     if (h->d_ctr) cudaFree(h->d_ctr);
     if (h->h_error) cudaFreeHost(h->h_error);
     if (h->staging) cudaFree(h->staging);
+    if (h->io.ok) {
+        cudaStreamSynchronize(h->io.s_in), cudaStreamSynchronize(h->io.s_out);
+        for (int b = 0; b < 2; ++b) {
+            cudaFree(h->io.in[b]), cudaFree(h->io.out[b]);
+            cudaEventDestroy(h->io.in_ready[b]), cudaEventDestroy(h->io.in_free[b]);
+            cudaEventDestroy(h->io.out_ready[b]), cudaEventDestroy(h->io.out_free[b]);
+        }
+        cudaStreamDestroy(h->io.s_in), cudaStreamDestroy(h->io.s_out);
+    }
     cudaFree(h->sort.keys_a);
     cudaFree(h->sort.keys_b);
     cudaFree(h->sort.vals_a);
@@ -752,6 +772,10 @@ static int poll_error(nmpm_sim* h) {
 static int sync_and_check(nmpm_sim* h) {
     CUDA_TRY(h, cudaMemcpyAsync(h->h_error, h->d_error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->io.ok) {  // pipelined host I/O in flight
+        CUDA_TRY(h, cudaStreamSynchronize(h->io.s_in));
+        CUDA_TRY(h, cudaStreamSynchronize(h->io.s_out));
+    }
     return poll_error(h);
 }
 
@@ -1005,6 +1029,112 @@ int nmpm_upload_particles(nmpm_handle h, const float* x, const float* v, const f
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     *h->h_error = 0;
     h->error_latched = false;
+    return NMPM_OK;
+}
+
+static int async_io_init(nmpm_sim* h) {
+    if (h->io.ok) return NMPM_OK;
+    const size_t D = (size_t) h->dim;
+    h->io.bytes = (h->n ? h->n : 1) * (2 * D + 2 * D * D + 1) * sizeof(float);
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->io.s_in, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->io.s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        CUDA_TRY(h, cudaMalloc(&h->io.in[b], h->io.bytes));
+        CUDA_TRY(h, cudaMalloc(&h->io.out[b], h->io.bytes));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->io.in_ready[b], cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->io.in_free[b], cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->io.out_ready[b], cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->io.out_free[b], cudaEventDisableTiming));
+    }
+    h->io.ok = true;
+    return NMPM_OK;
+}
+
+// Pipelined form of nmpm_upload_particles: returns as soon as the copies are enqueued.  The host arrays (pinned memory
+// for real overlap) must stay untouched until nmpm_synchronize or until two more async uploads have been issued.
+int nmpm_upload_particles_async(nmpm_handle h, const float* x, const float* v, const float* F, const float* C, const float* Jp) {
+    if (!h || (h->n && !x)) return NMPM_ERR_INVALID;
+    if (int rc = not_for_slabs(h, "nmpm_upload_particles_async")) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = h->n, D = (size_t) h->dim;
+    if (n == 0) return NMPM_OK;
+    if (int rc = async_io_init(h)) return rc;
+    const int b = (int) (h->io.k_in++ & 1u);
+    CUDA_TRY(h, cudaStreamWaitEvent(h->io.s_in, h->io.in_free[b], 0));  // the import that last read this buffer is done
+    float* p = h->io.in[b];
+    cudaError_t e = cudaSuccess;
+    auto up = [&](const float* src, size_t cnt) -> float* {
+        if (!src) return nullptr;
+        float* dst = p;
+        p += cnt;
+        cudaError_t ee = cudaMemcpyAsync(dst, src, cnt * sizeof(float), cudaMemcpyHostToDevice, h->io.s_in);
+        if (ee != cudaSuccess) e = ee;
+        return dst;
+    };
+    float* dx = up(x, n * D);
+    float* dv = up(v, n * D);
+    float* dF = up(F, n * D * D);
+    float* dC = up(C, n * D * D);
+    float* dJ = up(Jp, n);
+    CUDA_TRY(h, e);
+    CUDA_TRY(h, cudaEventRecord(h->io.in_ready[b], h->io.s_in));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->io.in_ready[b], 0));
+    ParticleStore& S = h->store[h->cur];
+    ParticleStore& T = h->store[h->cur ^ 1];
+    if (h->phase_next != 0) {  // see nmpm_upload_particles
+        NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + h->box_cur, h->P.n1)));
+        h->launches++;
+    }
+    NMPM_DISPATCH_DIM(h, (k_restore_constants<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(S, T, (uint32_t) n)));
+    NMPM_DISPATCH_DIM(h, (k_import_soa<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(dx, dv, dF, dC, dJ, nullptr, nullptr,
+                                                                                     (uint32_t) n, T, 1)));
+    h->launches += 2;
+    CUDA_TRY(h, cudaEventRecord(h->io.in_free[b], h->stream));
+    h->cur ^= 1;
+    h->phase_next = 0;
+    h->keys_valid = false;
+    h->box_valid = false;
+    h->perm = nullptr;
+    h->steps_done = 0;
+    // an error latched by earlier steps stays latched (no host wait here); the device flag starts clean for the new state
+    CUDA_TRY(h, cudaMemsetAsync(h->d_error, 0, sizeof(int), h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    return NMPM_OK;
+}
+
+// Pipelined form of nmpm_download_particles: the state as of the steps enqueued so far, in input order; the host arrays
+// are valid after nmpm_synchronize (or once two more async downloads have completed).
+int nmpm_download_particles_async(nmpm_handle h, float* x, float* v, float* F, float* C, float* Jp) {
+    if (!h) return NMPM_ERR_INVALID;
+    if (int rc = not_for_slabs(h, "nmpm_download_particles_async")) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = h->n, D = (size_t) h->dim;
+    if (n == 0) return NMPM_OK;
+    if (int rc = async_io_init(h)) return rc;
+    const int b = (int) (h->io.k_out++ & 1u);
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->io.out_free[b], 0));  // the D2H copy that last read this buffer is done
+    float* p = h->io.out[b];
+    float* dx = x ? p : nullptr;
+    p += x ? n * D : 0;
+    float* dv = v ? p : nullptr;
+    p += v ? n * D : 0;
+    float* dF = F ? p : nullptr;
+    p += F ? n * D * D : 0;
+    float* dC = C ? p : nullptr;
+    p += C ? n * D * D : 0;
+    float* dJ = Jp ? p : nullptr;
+    NMPM_DISPATCH_DIM(h, (k_export_soa<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(h->store[h->cur], (uint32_t) n, dx, dv, dF, dC,
+                                                                                     dJ, nullptr, nullptr)));
+    h->launches++;
+    CUDA_TRY(h, cudaEventRecord(h->io.out_ready[b], h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->io.s_out, h->io.out_ready[b], 0));
+    if (x) CUDA_TRY(h, cudaMemcpyAsync(x, dx, n * D * sizeof(float), cudaMemcpyDeviceToHost, h->io.s_out));
+    if (v) CUDA_TRY(h, cudaMemcpyAsync(v, dv, n * D * sizeof(float), cudaMemcpyDeviceToHost, h->io.s_out));
+    if (F) CUDA_TRY(h, cudaMemcpyAsync(F, dF, n * D * D * sizeof(float), cudaMemcpyDeviceToHost, h->io.s_out));
+    if (C) CUDA_TRY(h, cudaMemcpyAsync(C, dC, n * D * D * sizeof(float), cudaMemcpyDeviceToHost, h->io.s_out));
+    if (Jp) CUDA_TRY(h, cudaMemcpyAsync(Jp, dJ, n * sizeof(float), cudaMemcpyDeviceToHost, h->io.s_out));
+    CUDA_TRY(h, cudaEventRecord(h->io.out_free[b], h->io.s_out));
+    CUDA_TRY(h, cudaGetLastError());
     return NMPM_OK;
 }
 

@@ -87,6 +87,8 @@ def load_library():
     sig("nmpm_download_grid", ci, [vp, _fp, _fp, ct.POINTER(sz)])
     sig("nmpm_download_grid_aos", ci, [vp, vp, sz, ct.POINTER(sz)])
     sig("nmpm_upload_particles", ci, [vp] + [_fp] * 5)
+    sig("nmpm_upload_particles_async", ci, [vp] + [_fp] * 5)
+    sig("nmpm_download_particles_async", ci, [vp] + [_fp] * 5)
     sig("nmpm_num_particles", sz, [vp])
     sig("nmpm_grid_cells", sz, [vp])
     sig("nmpm_lame", ci, [vp, _fp, _fp])
@@ -288,6 +290,22 @@ class MPMSimulation:
         n, d = self.n, self.dim
         arrs = [_f32(x, (n, d)), _f32(v, (n, d)), _f32(F, (n, d, d)), _f32(C, (n, d, d)), _f32(Jp, (n,))]
         self._check(self._L.nmpm_upload_particles(self._h, *[_p(a) for a in arrs]), "nmpm_upload_particles")
+
+    def upload_async(self, x, v=None, F=None, C=None, Jp=None) -> None:
+        """Enqueue-only upload (nmpm_upload_particles_async).  The arrays must be float32, C-contiguous, of the right
+        shape (no conversion copies are made: they would be freed before the copy runs) and stay alive until
+        synchronize(); pinned memory gives real overlap."""
+        for a, shape in ((x, (self.n, self.dim)), (v, (self.n, self.dim)), (F, (self.n, self.dim, self.dim)),
+                         (C, (self.n, self.dim, self.dim)), (Jp, (self.n,))):
+            if a is not None and (a.dtype != np.float32 or not a.flags.c_contiguous or a.shape != shape):
+                raise ValueError("upload_async needs C-contiguous float32 arrays of the particle shapes")
+        self._check(self._L.nmpm_upload_particles_async(self._h, *[_p(a) for a in (x, v, F, C, Jp)]),
+                    "nmpm_upload_particles_async")
+
+    def download_async(self, out: dict) -> None:
+        """Enqueue-only download into preallocated arrays out[x|v|F|C|Jp] (valid after synchronize())."""
+        self._check(self._L.nmpm_download_particles_async(self._h, *[_p(out.get(k)) for k in ("x", "v", "F", "C", "Jp")]),
+                    "nmpm_download_particles_async")
 
     def sort_debug(self) -> dict:
         n, d = self.n, self.dim
