@@ -259,7 +259,8 @@ def run_gpu(args):
     # ---- device-resident timing -------------------------------------------------------------
     # advance() replays one CUDA graph per host-side step state (2 * sort_every of them): run through the cycle once
     # so that no capture / instantiation lands in the warm-up or in the timed region
-    prime = 2 * max(1, args.sort_every)
+    # (and the 8-step cycle graph nmpm_advance uses for runs of steps: 4 cycles in one call capture it)
+    prime = 8 * max(1, args.sort_every)
     sim.advance(prime)
     sim.advance(args.warmup)
     sync()

@@ -781,31 +781,36 @@ static int sync_and_check(nmpm_sim* h) {
 
 extern "C" {
 
-// One whole step.  With opt.use_graph the launch sequence of each distinct host-side step state is
-// captured once into a CUDA graph and replayed afterwards (one launch per step instead of ~12).
-static int step_once(nmpm_sim* h) {
+// `count` whole steps.  With opt.use_graph the launch sequence of each distinct host-side step state is captured once
+// into a CUDA graph and replayed afterwards (one launch per step instead of ~12) — and, for runs of steps, a whole CYCLE
+// of host states (sort cadence x store parity x node-box ring: 8 steps at the default cadence) is captured into ONE graph,
+// so a small scene costs the host one launch per 8 steps (config 5: thousands of steps of 1 250-particle scenes).
+static int graph_steps(nmpm_sim* h, int count) {
     const bool can_graph = h->opt.use_graph && h->graphs_ok && !h->timing && h->phase_next == 0 && h->n > 0;
     if (!can_graph) {
-        for (int ph = h->phase_next; ph < 3; ++ph)
-            if (int rc = run_phase(h, ph)) return rc;
-        h->phase_next = 0;
+        for (int k = 0; k < count; ++k) {
+            for (int ph = h->phase_next; ph < 3; ++ph)
+                if (int rc = run_phase(h, ph)) return rc;
+            h->phase_next = 0;
+        }
         return NMPM_OK;
     }
     const int se = h->opt.sort_every;
     const int box0 = h->box_cur;
     const bool boxv0 = h->box_valid;
     const int key = h->cur | (h->keys_valid ? 2 : 0) | (box0 << 2) | (boxv0 ? 16 : 0) |
-                    ((se > 0 ? (int) (h->steps_done % se) : 0) << 5);
+                    ((se > 0 ? (int) (h->steps_done % se) : 0) << 5) | (count << 12);
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
         if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
             cudaGetLastError();
             h->graphs_ok = false;  // e.g. the legacy default stream: fall back to plain launches
-            return step_once(h);
+            return graph_steps(h, count);
         }
         const long long l0 = h->launches, s0 = h->steps_done;
         int rc = NMPM_OK;
-        for (int ph = 0; ph < 3 && rc == NMPM_OK; ++ph) rc = run_phase(h, ph);
+        for (int k = 0; k < count && rc == NMPM_OK; ++k)
+            for (int ph = 0; ph < 3 && rc == NMPM_OK; ++ph) rc = run_phase(h, ph);
         cudaGraph_t g = nullptr;
         cudaError_t e = cudaStreamEndCapture(h->stream, &g);
         nmpm_sim::StepGraph sg;
@@ -815,7 +820,7 @@ static int step_once(nmpm_sim* h) {
             cudaGetLastError();
             h->graphs_ok = false;
             h->last_error = "CUDA graph capture failed; falling back to plain launches";
-            // host-side state already advanced by the capture pass: undo and run the step for real
+            // host-side state already advanced by the capture pass: undo and run the steps for real
             h->steps_done = s0;
             h->launches = l0;
             h->cur = key & 1;
@@ -823,7 +828,7 @@ static int step_once(nmpm_sim* h) {
             h->box_cur = box0;
             h->box_valid = boxv0;
             h->perm = nullptr;
-            return step_once(h);
+            return graph_steps(h, count);
         }
         sg.cur_after = h->cur;
         sg.keys_valid_after = h->keys_valid;
@@ -840,9 +845,17 @@ static int step_once(nmpm_sim* h) {
     h->box_valid = true;
     h->perm = nullptr;
     h->grid_valid = true;
-    h->steps_done++;
+    h->steps_done += count;
     h->launches += it->second.launches;
     return NMPM_OK;
+}
+
+// host states repeat with this period (sort cadence x store parity, node-box ring)
+static int graph_cycle(const nmpm_sim* h) {
+    const int se = h->opt.sort_every;
+    int c = se > 0 ? 2 * se : 1;
+    while (c % kBoxRing) c += (se > 0 ? 2 * se : 1);
+    return c;
 }
 
 static int not_for_slabs(nmpm_sim* h, const char* what) {
@@ -858,8 +871,13 @@ int nmpm_advance(nmpm_handle h, int nsteps) {
     if (int rc = not_for_slabs(h, "nmpm_advance")) return rc;
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (int rc = poll_error(h)) return rc;
-    for (int s = 0; s < nsteps; ++s)
-        if (int rc = step_once(h)) return rc;
+    const int cyc = graph_cycle(h);
+    for (int s = 0; s < nsteps;) {
+        // whole cycles in one graph once the state is periodic (keys and box valid: i.e. not the very first step)
+        const int k = (nsteps - s >= cyc && cyc <= 64 && h->steps_done >= cyc && h->steps_done % cyc == 0) ? cyc : 1;
+        if (int rc = graph_steps(h, k)) return rc;
+        s += k;
+    }
     CUDA_TRY(h, cudaMemcpyAsync(h->h_error, h->d_error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     return NMPM_OK;
 }
