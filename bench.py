@@ -55,6 +55,10 @@ def scene(name: str):
 
 # algorithmic bytes per particle-step: P2G reads S+2 floats, G2P reads x,F,Jp and writes S
 ALGO_BYTES = {3: dict(p2g=108, g2p=152), 2: dict(p2g=60, g2p=80)}
+# Fused G2P+P2G (nmpm_fused.cuh): ONE launch does the G2P of step n and the P2G of step n+1.  Its algorithmic bytes by
+# SURVEY.md §8(d)'s per-unit figures are the sum (260 B: what the two phases move when they are separate passes);
+# the bytes the fused pass itself has to move are 160 B per particle (read x,F,Jp,mass,volume = 60, write the state = 100).
+FUSED_MIN_BYTES = {3: 160}
 
 
 class ClockSampler:
@@ -249,8 +253,10 @@ def run_gpu(args):
         return
 
     stream = torch.cuda.Stream()
-    sim = nm.MPMSimulation(x, model, res, device=local, sort_every=args.sort_every, p2g_variant=args.p2g_variant)
+    sim = nm.MPMSimulation(x, model, res, device=local, sort_every=args.sort_every, p2g_variant=args.p2g_variant,
+                           fuse=args.fuse)
     sim.set_stream(stream.cuda_stream)
+    fused = bool(sim.fused)
 
     def sync():
         sim.synchronize()
@@ -292,9 +298,17 @@ def run_gpu(args):
         sim.timing_enable(False)
         steps_done += args.steps + prof_steps
         phases = {k + "_ms": tm[k] / max(1, tm["steps"]) for k in ("sort", "p2g", "grid", "g2p")}
-        kern = {k: {"ms": phases[k + "_ms"],
-                    "achieved_GBps": ab[k] * n_total / (phases[k + "_ms"] * 1e-3) / 1e9 if phases[k + "_ms"] > 0 else 0.0}
-                for k in ("p2g", "g2p")}
+        if fused:
+            # g2p_ms is the fused launch (G2P of step n + P2G of step n+1); p2g_ms is what is left of the P2G phase
+            # (buffer swap + clear of the other grid)
+            t = phases["g2p_ms"] * 1e-3
+            kern = {"g2p_p2g": {"ms": phases["g2p_ms"],
+                                "achieved_GBps": (ab["p2g"] + ab["g2p"]) * n_total / t / 1e9 if t > 0 else 0.0,
+                                "min_traffic_GBps": FUSED_MIN_BYTES[dim] * n_total / t / 1e9 if t > 0 else 0.0}}
+        else:
+            kern = {k: {"ms": phases[k + "_ms"],
+                        "achieved_GBps": ab[k] * n_total / (phases[k + "_ms"] * 1e-3) / 1e9 if phases[k + "_ms"] > 0 else 0.0}
+                    for k in ("p2g", "g2p")}
         for k in kern:
             kern[k]["frac"] = kern[k]["achieved_GBps"] / peak
         return {"steps": [first, first + args.steps], "value": n_total * args.steps / (ms * 1e-3),
@@ -305,12 +319,18 @@ def run_gpu(args):
     clocks = clk.summary()
     value, ms, launches = early["value"], early["ms_per_step"] * args.steps, early["launches"]
     phases = early["phase_ms"]
-    dom = "g2p" if phases["g2p_ms"] >= phases["p2g_ms"] else "p2g"
+    dom = "g2p_p2g" if fused else ("g2p" if phases["g2p_ms"] >= phases["p2g_ms"] else "p2g")
     achieved = early["kernels"][dom]["achieved_GBps"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
                 "traffic": ncu_traffic(dom, n_total) if dim == 3 else None, "peak_source": peak_src,
-                "algorithmic_bytes_per_particle": ab[dom], "other": early["kernels"], "phase_ms": phases}
+                "algorithmic_bytes_per_particle": (ab["p2g"] + ab["g2p"]) if fused else ab[dom],
+                "other": early["kernels"], "phase_ms": phases}
+    if fused:
+        roofline["what"] = ("one launch = G2P of step n + P2G of step n+1 (nmpm_fused.cuh): algorithmic bytes = SURVEY 8(d)'s "
+                            "108 (P2G) + 152 (G2P) per particle; frac_min_traffic counts only the 160 B per particle the fused "
+                            "pass itself must move")
+        roofline["frac_min_traffic"] = early["kernels"][dom]["min_traffic_GBps"] / peak
 
     # ---- late phase (under Q1 the snow turns into a particle gas that fills the box) ----
     late = None
@@ -372,7 +392,7 @@ def run_gpu(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": bench_config(args, desc, n_total, res, dim, model),
         "run": {"sort_every": args.sort_every, "graph_priming_steps": prime, "p2g_variant": args.p2g_variant,
-                "timed_steps": early["steps"]},
+                "fused_g2p_p2g": fused, "timed_steps": early["steps"]},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "phases": {"early": early, "late": late},
     }
@@ -388,6 +408,7 @@ def main():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--sort-every", type=int, default=4)
     ap.add_argument("--p2g-variant", type=int, default=0)
+    ap.add_argument("--fuse", type=int, default=0, help="nmpm_options.fuse: 0 auto (on in 3D), 1 off, 2 on, 3 always")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-full-check", action="store_true", help="--impl reference: skip the 2 real full-scene steps")
     ap.add_argument("--late-step", type=int, default=-1,

@@ -65,7 +65,12 @@ typedef struct nmpm_options {
                          window while the current chunk computes.  Env NMPM_G2P_WINDOW=0/1/2 (= modes 1/2/3) overrides.
                          Every mode reads the same nodes (same results).  Measured on cfg4: mode 1 is the fastest
                           and is what 0 selects */
-    int reserved[8];
+    int fuse;         /* 3D, single GPU, with binning: G2P of step n also scatters step n+1 (P2G) into a second grid while
+                         the particle is in registers (nmpm_fused.cuh) - 160 B instead of 260 B per particle and step.
+                         0 = auto (on), 1 = off, 2 = on except for the first step after an upload (the uploaded state is
+                         likely to be replaced again: teacher-forced loops), 3 = always.  Env NMPM_FUSE=0/1/2 (= 1/2/3)
+                         overrides.  Results: same sums in a different floating-point order (like any sort cadence) */
+    int reserved[7];
 } nmpm_options;
 
 void nmpm_default_options(nmpm_options *opt);
@@ -154,6 +159,9 @@ int nmpm_timing_enable(nmpm_handle h, int on);
 int nmpm_timing_read(nmpm_handle h, float *ms /* NMPM_T_COUNT */, int *steps, int reset);
 /* number of kernel launches issued by the library for this sim since creation */
 long long nmpm_launch_count(nmpm_handle h);
+/* 1 (or 2 = also right after an upload) when this sim runs the fused G2P+P2G kernel (nmpm_options.fuse), else 0: the
+ * NMPM_T_G2P timer then covers G2P of step n AND the P2G scatter of step n+1, NMPM_T_P2G only the buffer swap + clear */
+int nmpm_fused(nmpm_handle h);
 
 /* Stream plumbing: run on an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream). */
 int nmpm_set_stream(nmpm_handle h, void *cuda_stream);

@@ -16,6 +16,7 @@
 #include "../../include/nmpm.h"
 #include "nmpm_kernels.cuh"
 #include "nmpm_p2g_cell.cuh"
+#include "nmpm_fused.cuh"
 #include "nmpm_sort.cuh"
 
 using namespace nmpm;
@@ -57,6 +58,13 @@ struct nmpm_sim {
     ParticleStore store[2]{};
     int cur = 0;
     float4* grid = nullptr;
+    // Fused G2P+P2G (nmpm_fused.cuh; 3D, single GPU): the G2P of step n scatters step n+1 into `grid_alt`; the next step's
+    // P2G phase swaps the two buffers.  Invariant: outside [fused launch, next P2G phase] `grid_alt` is all zero.
+    float4* grid_alt = nullptr;
+    int fuse = 0;            // 0 off, 1 on (not on the first step after an upload: that state may be replaced again), 2 always
+    bool p2g_ahead = false;  // grid_alt holds the P2G of store[cur] (the coming step) over box[box_cur]
+    int grid_sel = 0;        // which of the two buffers `grid` is (CUDA-graph key)
+    int fused_minb = NMPM_FUSED_MINB;  // CTAs per SM the fused kernel is compiled for (env NMPM_FUSED_MINB: experiments)
     // node boxes (GridBox, device): box[box_cur] bounds the particles of the current step, box[(box_cur+3)%4]
     // the nodes the previous P2G wrote (cleared at the start of the next one), box[(box_cur+1)%4] is being
     // built by the G2P in flight
@@ -110,6 +118,8 @@ struct nmpm_sim {
         int cur_after = 0;
         int box_after = 0;
         bool keys_valid_after = false;
+        bool ahead_after = false;
+        int grid_sel_after = 0;
         int launches = 0;
     };
     std::unordered_map<int, StepGraph> graphs;
@@ -326,11 +336,22 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
         h->g2p_window = mode >= 2 && make_grid_map(h) == NMPM_OK;  // no tensor map: plain global gather
         h->g2p_pipe = h->g2p_window && mode == 3;
     }
+    {   // fused G2P+P2G: 3D, single GPU, binned, global gather
+        int mode = h->opt.fuse;  // 0 auto, 1 off, 2 on, 3 always
+        if (const char* fz = std::getenv("NMPM_FUSE")) mode = (*fz >= '0' && *fz <= '2') ? (*fz - '0') + 1 : mode;
+        if (mode == 0) mode = 2;
+        h->fuse = (dim == 3 && !h->slab && h->opt.sort_every > 0 && !h->g2p_window && mode >= 2) ? mode - 1 : 0;
+        if (const char* mb = std::getenv("NMPM_FUSED_MINB")) h->fused_minb = std::atoi(mb);
+        if (h->fuse) {
+            CUDA_TRY(h, cudaMalloc(&h->grid_alt, h->cells * sizeof(float4)));
+            CUDA_TRY(h, cudaMemset(h->grid_alt, 0, h->cells * sizeof(float4)));
+        }
+    }
     CUDA_TRY(h, cudaMalloc(&h->d_box, kBoxRing * sizeof(GridBox)));
     CUDA_TRY(h, cudaMalloc(&h->d_box_partial, ((h->cap + 127) / 128 * 4 + 4) * 8 * sizeof(int)));
     for (int k = 0; k < kBoxRing; ++k) k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + k);
-    CUDA_TRY(h, cudaMalloc(&h->d_error, sizeof(int)));
-    CUDA_TRY(h, cudaMemset(h->d_error, 0, sizeof(int)));
+    CUDA_TRY(h, cudaMalloc(&h->d_error, 2 * sizeof(int)));  // [0] this step, [1] found ahead by the fused scatter
+    CUDA_TRY(h, cudaMemset(h->d_error, 0, 2 * sizeof(int)));
     CUDA_TRY(h, cudaMallocHost(&h->h_error, sizeof(int)));
     *h->h_error = 0;
     // sort workspace
@@ -384,6 +405,7 @@ void nmpm_destroy(nmpm_handle h) {
     free_store(h->store[0]);
     free_store(h->store[1]);
     if (h->grid) cudaFree(h->grid);
+    if (h->grid_alt) cudaFree(h->grid_alt);
     if (h->d_box) cudaFree(h->d_box);
     if (h->d_box_partial) cudaFree(h->d_box_partial);
     if (h->d_error) cudaFree(h->d_error);
@@ -528,6 +550,7 @@ size_t nmpm_grid_cells(nmpm_handle h) { return h ? h->cells : 0; }
 size_t nmpm_num_slots(nmpm_handle h) { return h ? h->n_store : 0; }
 int nmpm_key_tile_bits(nmpm_handle) { return kTileBits; }
 long long nmpm_launch_count(nmpm_handle h) { return h ? h->launches : 0; }
+int nmpm_fused(nmpm_handle h) { return h ? h->fuse : 0; }
 
 int nmpm_lame(nmpm_handle h, float* mu_0, float* lambda_0) {
     if (!h) return NMPM_ERR_INVALID;
@@ -603,7 +626,29 @@ static int ensure_box(nmpm_sim* h) {
     return NMPM_OK;
 }
 
+// The particle state is about to be replaced (upload): the sums the last fused G2P scattered ahead into grid_alt belong to
+// the old state.  They cover box[box_cur]; zero them (before the key pass of the new state resets that box).
+static void discard_p2g_ahead(nmpm_sim* h) {
+    if (!h->p2g_ahead) return;
+    NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid_alt, h->d_box + h->box_cur, h->P.n1)));
+    h->launches++;
+    h->p2g_ahead = false;
+}
+
 static int do_p2g(nmpm_sim* h) {
+    if (h->p2g_ahead) {
+        // the previous step's fused G2P already scattered this step into grid_alt: swap the buffers, take over what its
+        // scatter half found, and zero the grid of the previous step (now grid_alt) over the box its P2G wrote
+        std::swap(h->grid, h->grid_alt);
+        h->grid_sel ^= 1;
+        h->p2g_ahead = false;
+        k_promote_error<<<1, 32, 0, h->stream>>>(h->d_error);
+        NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(
+                                 h->grid_alt, h->d_box + (h->box_cur + kBoxRing - 1) % kBoxRing, h->P.n1)));
+        h->launches += 2;
+        h->grid_valid = true;
+        return NMPM_OK;
+    }
     if (int rc = ensure_box(h)) return rc;
     // K1: clear what the previous P2G (and, for a slab, the neighbours' ghost planes) wrote
     NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + (h->box_cur + kBoxRing - 1) % kBoxRing,
@@ -673,7 +718,20 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
     const uint32_t* gone_keys = (h->dev_counts || (h->slab && !h->perm && h->n_gone)) ? h->sort.keys_a : nullptr;
     const int box_next = (h->box_cur + 1) % kBoxRing;
     k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + box_next);
-    if (h->g2p_window && h->g2p_pipe) {  // 3D only: persistent CTAs, pipelined rows (cp.async) and node windows (TMA)
+    // fused G2P+P2G: not on the first step after an upload (fuse == 1) — that state is likely to be replaced again
+    const bool fused = h->fuse && !mig.left && (h->fuse == 2 || h->steps_done > 0);
+    if (fused) {
+        if (h->model == 0)
+            launch_g2p_p2g<0>(S, T, h->perm, n, h->P, h->grid, h->grid_alt, keys_out, h->tiles_per_axis, h->d_error,
+                              h->d_box_partial, h->local_reorder ? 1 : 0, h->stream, h->fused_minb);
+        else if (h->model == 1)
+            launch_g2p_p2g<1>(S, T, h->perm, n, h->P, h->grid, h->grid_alt, keys_out, h->tiles_per_axis, h->d_error,
+                              h->d_box_partial, h->local_reorder ? 1 : 0, h->stream, h->fused_minb);
+        else
+            launch_g2p_p2g<2>(S, T, h->perm, n, h->P, h->grid, h->grid_alt, keys_out, h->tiles_per_axis, h->d_error,
+                              h->d_box_partial, h->local_reorder ? 1 : 0, h->stream, h->fused_minb);
+        h->p2g_ahead = true;
+    } else if (h->g2p_window && h->g2p_pipe) {  // 3D only: persistent CTAs, pipelined rows (cp.async) and node windows (TMA)
         const unsigned chunks = blocks_for(n, 128);
         const unsigned grid_ctas = chunks < (unsigned) (148 * NMPM_G2P_PIPE_MINB) ? chunks : (unsigned) (148 * NMPM_G2P_PIPE_MINB);
         if (h->model == 0)
@@ -798,8 +856,11 @@ static int graph_steps(nmpm_sim* h, int count) {
     const int se = h->opt.sort_every;
     const int box0 = h->box_cur;
     const bool boxv0 = h->box_valid;
+    const bool ahead0 = h->p2g_ahead;
+    const int gsel0 = h->grid_sel;
     const int key = h->cur | (h->keys_valid ? 2 : 0) | (box0 << 2) | (boxv0 ? 16 : 0) |
-                    ((se > 0 ? (int) (h->steps_done % se) : 0) << 5) | (count << 12);
+                    ((se > 0 ? (int) (h->steps_done % se) : 0) << 5) | (count << 12) | (ahead0 ? 1 << 20 : 0) | (gsel0 << 21) |
+                    ((h->fuse == 1 && h->steps_done == 0) ? 1 << 22 : 0);
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
         if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
@@ -828,11 +889,15 @@ static int graph_steps(nmpm_sim* h, int count) {
             h->box_cur = box0;
             h->box_valid = boxv0;
             h->perm = nullptr;
+            if (h->grid_sel != gsel0) std::swap(h->grid, h->grid_alt), h->grid_sel = gsel0;
+            h->p2g_ahead = ahead0;
             return graph_steps(h, count);
         }
         sg.cur_after = h->cur;
         sg.keys_valid_after = h->keys_valid;
         sg.box_after = h->box_cur;
+        sg.ahead_after = h->p2g_ahead;
+        sg.grid_sel_after = h->grid_sel;
         sg.launches = (int) (h->launches - l0);
         it = h->graphs.emplace(key, sg).first;
         CUDA_TRY(h, cudaGraphLaunch(it->second.exec, h->stream));
@@ -845,6 +910,8 @@ static int graph_steps(nmpm_sim* h, int count) {
     h->box_valid = true;
     h->perm = nullptr;
     h->grid_valid = true;
+    h->p2g_ahead = it->second.ahead_after;
+    if (h->grid_sel != it->second.grid_sel_after) std::swap(h->grid, h->grid_alt), h->grid_sel = it->second.grid_sel_after;
     h->steps_done += count;
     h->launches += it->second.launches;
     return NMPM_OK;
@@ -1021,6 +1088,7 @@ int nmpm_upload_particles(nmpm_handle h, const float* x, const float* v, const f
     CUDA_TRY(h, e);
     ParticleStore& S = h->store[h->cur];
     ParticleStore& T = h->store[h->cur ^ 1];
+    discard_p2g_ahead(h);
     if (h->phase_next != 0) {
         // Upload in the middle of a step (after nmpm_phase(P2G) or (GRID_OP)): the aborted step's P2G has already
         // written the nodes of box[box_cur], and the next step only clears box[box_cur-1] (which that P2G cleared
@@ -1041,7 +1109,7 @@ int nmpm_upload_particles(nmpm_handle h, const float* x, const float* v, const f
     h->perm = nullptr;
     // the sort cadence restarts so that the next step re-bins the new state
     h->steps_done = 0;
-    CUDA_TRY(h, cudaMemsetAsync(h->d_error, 0, sizeof(int), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_error, 0, 2 * sizeof(int), h->stream));
     // the host copy of the flag is reset only after the stream has drained: an error-flag copy of an earlier
     // nmpm_advance may still be in flight and would otherwise re-raise the old state's error for the new one
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1099,6 +1167,7 @@ int nmpm_upload_particles_async(nmpm_handle h, const float* x, const float* v, c
     CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->io.in_ready[b], 0));
     ParticleStore& S = h->store[h->cur];
     ParticleStore& T = h->store[h->cur ^ 1];
+    discard_p2g_ahead(h);
     if (h->phase_next != 0) {  // see nmpm_upload_particles
         NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + h->box_cur, h->P.n1)));
         h->launches++;
@@ -1115,7 +1184,7 @@ int nmpm_upload_particles_async(nmpm_handle h, const float* x, const float* v, c
     h->perm = nullptr;
     h->steps_done = 0;
     // an error latched by earlier steps stays latched (no host wait here); the device flag starts clean for the new state
-    CUDA_TRY(h, cudaMemsetAsync(h->d_error, 0, sizeof(int), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_error, 0, 2 * sizeof(int), h->stream));
     CUDA_TRY(h, cudaGetLastError());
     return NMPM_OK;
 }

@@ -46,7 +46,7 @@ class MaterialModel(enum.IntEnum):
 class Options(ct.Structure):
     _fields_ = [("device", ct.c_int), ("sort_every", ct.c_int), ("p2g_variant", ct.c_int), ("use_graph", ct.c_int),
                 ("slab_x0", ct.c_int), ("slab_x1", ct.c_int), ("capacity", ct.c_int), ("g2p_window", ct.c_int),
-                ("reserved", ct.c_int * 8)]
+                ("fuse", ct.c_int), ("reserved", ct.c_int * 7)]
 
 
 def lib_path() -> Path:
@@ -101,6 +101,7 @@ def load_library():
     sig("nmpm_timing_enable", ci, [vp, ci])
     sig("nmpm_timing_read", ci, [vp, _fp, ct.POINTER(ci), ci])
     sig("nmpm_launch_count", ct.c_longlong, [vp])
+    sig("nmpm_fused", ci, [vp])
     sig("nmpm_set_stream", ci, [vp, vp])
     sig("nmpm_get_stream", vp, [vp])
     sig("nmpm_grid_plane_ptr", vp, [vp, ci])
@@ -170,7 +171,7 @@ class MPMSimulation:
     def __init__(self, particles, model, res: int = 64, dt: float = 1e-4, E: float = 1e4, nu: float = 0.2,
                  gravity: float = -100.0, *, v=None, F=None, C=None, Jp=None, mass=None, volume=None,
                  device: int = 0, sort_every: int = 4, p2g_variant: int = 0, slab=None, capacity: int = 0,
-                 ids=None, g2p_window: int = 0):
+                 ids=None, g2p_window: int = 0, fuse: int = 0):
         self._L = load_library()
         x = _f32(particles)
         if x.ndim != 2 or x.shape[1] not in (2, 3):
@@ -181,6 +182,7 @@ class MPMSimulation:
         opt = Options()
         self._L.nmpm_default_options(C_byref(opt))
         opt.device, opt.sort_every, opt.p2g_variant, opt.g2p_window = device, sort_every, p2g_variant, g2p_window
+        opt.fuse = int(fuse)   # 0 auto, 1 off, 2 on (not on the first step after an upload), 3 always
         if slab is not None:
             opt.slab_x0, opt.slab_x1 = slab
             opt.capacity = int(capacity)
@@ -335,6 +337,11 @@ class MPMSimulation:
 
     def launch_count(self) -> int:
         return int(self._L.nmpm_launch_count(self._h))
+
+    @property
+    def fused(self) -> int:
+        """1/2 when G2P also scatters the next step's P2G (include/nmpm.h: nmpm_options.fuse), else 0"""
+        return int(self._L.nmpm_fused(self._h))
 
     def set_stream(self, cuda_stream: int) -> None:
         self._check(self._L.nmpm_set_stream(self._h, ct.c_void_p(cuda_stream)), "nmpm_set_stream")

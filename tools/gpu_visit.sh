@@ -9,6 +9,11 @@ for w in $what; do
 case $w in
 test)    timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_parity_fullres_gpu.py > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 $out/pytest_gpu.log;;
 fullres) rm -f gpurun_out/parity_fullres.md; timeout 1500 python -m pytest tests/test_parity_fullres_gpu.py -m gpu -q > $out/pytest_fullres.log 2>&1; echo "fullres rc=$?"; tail -15 $out/pytest_fullres.log; cp gpurun_out/parity_fullres.md $out/ 2>/dev/null;;
+fusedtest) timeout 600 python -m pytest tests/test_fused_gpu.py -m gpu -q > $out/pytest_fused.log 2>&1; echo "fused pytest rc=$?"; tail -25 $out/pytest_fused.log;;
+quickoff) timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --fuse 1 > $out/bench_quick_unfused.json 2> $out/bench_quick_unfused.err; echo "bench unfused rc=$?"; tail -3 $out/bench_quick_unfused.err; python tools/bench_summary.py $out/bench_quick_unfused.json;;
+abminb)  for mb in 5 8; do NMPM_FUSED_MINB=$mb timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --late-step 0 > $out/bench_minb$mb.json 2> $out/bench_minb$mb.err; echo "minb $mb rc=$?"; python tools/bench_summary.py $out/bench_minb$mb.json; done;;
+ncufused) timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_g2p_p2g' -s 28 -c 4 \
+            -f -o $out/prof_cfg4_fused python tools/profile_step.py --workload cfg4 --warmup 28 --steps 6 --sort-every 4 > $out/ncu_fused.log 2>&1; echo "ncu rc=$?"; tail -2 $out/ncu_fused.log;;
 smoke)   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $out/smoke.log;;
 bench)   timeout 900 python bench.py --steps 20 --warmup 5 > $out/bench_default.json 2> $out/bench_default.err; echo "bench rc=$?"; tail -3 $out/bench_default.err; python tools/bench_summary.py $out/bench_default.json;;
 quick)   timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu > $out/bench_quick.json 2> $out/bench_quick.err; echo "bench rc=$?"; tail -3 $out/bench_quick.err; python tools/bench_summary.py $out/bench_quick.json;;
