@@ -22,7 +22,7 @@
 #include "nmpm_p2g_cell.cuh"
 
 #ifndef NMPM_FUSED_MINB
-#define NMPM_FUSED_MINB 6
+#define NMPM_FUSED_MINB 8
 #endif
 
 namespace nmpm {
@@ -67,7 +67,30 @@ __global__ void __launch_bounds__(128, MINB) k_g2p_p2g(ParticleStore S, Particle
             g2p_gather3(nodes, w, fx, 4.0f * P.inv_dx, vn, Cn);
         }
         const float2 mv = S.mv[src];  // coherent loads: the re-grouping rewrites these arrays in place
-        g2p_update<D, MODEL>(p, Cn, vn, P);
+        // snow: the plasticity projection of this G2P already holds the SVD of the new F — the stress of step n+1 is built
+        // from its factors (affine_matrix_snow_factors) instead of a second polar decomposition
+        [[maybe_unused]] SvdFactors sf;
+        [[maybe_unused]] bool have_sf = false;
+        if constexpr (MODEL == 0) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                p.v[d] = vn[d];
+                p.x[d] = fmaf(P.dt, vn[d], p.x[d]);  // advection (src/nclr.h:229)
+            }
+            p.C = Cn;
+            Mat<D> M;  // F' = (diag<dim>(1) + dt*C) * F   (Q1)
+#pragma unroll
+            for (int q = 0; q < D * D; ++q) M.m[q] = P.dt * Cn.m[q];
+            M(0, 0) += 1.0f;
+            M(1, 1) += 1.0f;
+            Mat<D> Fn = mat_mul<D>(M, p.F);
+            const float old_J = det(Fn);
+            have_sf = snow_project_factors(Fn, 0.975f, 1.0045f, p.F, sf);  // U clamp(sig) V^T (src/nclr.h:239-247)
+            const float new_J = have_sf ? sf.f[0] * sf.f[1] * sf.f[2] : det(p.F);
+            p.Jp = clampf(p.Jp * old_J / new_J, 0.6f, 20.0f);
+        } else {
+            g2p_update<D, MODEL>(p, Cn, vn, P);
+        }
 
         // ---- bin the advected particle: cell key of step n+1, rank inside the warp ------------------------------
         int b[D];
@@ -110,7 +133,14 @@ __global__ void __launch_bounds__(128, MINB) k_g2p_p2g(ParticleStore S, Particle
         const uint32_t dst = (i - lane) + (uint32_t) rank;
 
         // ---- stress of the new state (k_p2g_cols phase A) ------------------------------------------------------
-        const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, mv.x, mv.y, P);
+        Mat<D> A;
+        if constexpr (MODEL == 0) {
+            if (have_sf) A = affine_matrix_snow_factors(sf, p.C, p.Jp, mv.x, mv.y, P);
+            else
+                A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, mv.x, mv.y, P);
+        } else {
+            A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, mv.x, mv.y, P);
+        }
         store_state<D>(T, dst, p);
         if (perm || moved) {
             T.mv[dst] = mv;
@@ -158,10 +188,13 @@ __global__ void __launch_bounds__(128, MINB) k_g2p_p2g(ParticleStore S, Particle
     __syncwarp();
 
     // ---- P2G of step n+1 (k_p2g_cols phase B: lane = group g, stencil column (j,k); nodes i = 0,1,2 in registers) ----
+    // (Cutting the thirds at run heads instead of at 11/22 saves two flushes per warp but costs as many issue slots as
+    // it saves LSU cycles: measured +-0 on cfg4, gpurun r2s.)
+    constexpr int s1 = 11, s2 = 22;
     if (lane >= 27) return;
     const int g = lane / 9, jk = lane - 9 * g, j = jk / 3, k = jk - 3 * j;
-    const int s_begin = 11 * g;
-    const int s_end = min((g == 2) ? 32 : s_begin + 11, cnt);
+    const int s_begin = (g == 0) ? 0 : (g == 1) ? s1 : s2;
+    const int s_end = min((g == 0) ? s1 : (g == 1) ? s2 : 32, cnt);
     if (s_begin >= s_end) return;
     const uint32_t plane = (uint32_t) (n1 * n1);
     const uint32_t col = (uint32_t) (j * n1 + k);

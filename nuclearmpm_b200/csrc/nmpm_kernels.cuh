@@ -155,13 +155,15 @@ __global__ void k_box_reset(GridBox* __restrict__ box) {
 }
 
 // node box [lo, hi+2] clipped to the grid; returns the number of nodes (0 for an empty box)
+// `n1x`: node rows along x (scenes * n1 for a batch of stacked 2D scenes; 0 = n1)
 template <int D>
-__device__ __forceinline__ uint32_t box_extent(const GridBox* __restrict__ box, int n1, int (&lo)[D], uint32_t (&ext)[D]) {
+__device__ __forceinline__ uint32_t box_extent(const GridBox* __restrict__ box, int n1, int (&lo)[D], uint32_t (&ext)[D],
+                                               int n1x = 0) {
     uint32_t vol = 1;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const int l = max(box->lo[d], 0);
-        const int h = min(box->hi[d] + 2, n1 - 1);
+        const int h = min(box->hi[d] + 2, ((d == 0 && n1x > 0) ? n1x : n1) - 1);
         if (h < l) return 0;
         lo[d] = l;
         ext[d] = (uint32_t) (h - l + 1);
@@ -189,13 +191,32 @@ __device__ __forceinline__ size_t box_node(uint32_t i, const int (&lo)[D], const
 
 // ---- K1: clear the nodes the previous P2G wrote (grid-stride over the previous box) ----------
 template <int D>
-__global__ void __launch_bounds__(256) k_clear_box(float4* __restrict__ grid, const GridBox* __restrict__ box, int n1) {
+__global__ void __launch_bounds__(256) k_clear_box(float4* __restrict__ grid, const GridBox* __restrict__ box, int n1,
+                                                   int n1x = 0) {
     int lo[D], c[D];
     uint32_t ext[D];
-    const uint32_t vol = box_extent<D>(box, n1, lo, ext);
+    const uint32_t vol = box_extent<D>(box, n1, lo, ext, n1x);
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < vol; i += stride)
         grid[box_node<D>(i, lo, ext, n1, c)] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// Batch of stacked 2D scenes (MaterialParams::scenes): scene of the particle in slot `slot`, and the node-row offset
+// that turns its base.x into the stacked grid's.  Single scene / 3D: 0.
+template <int D>
+__device__ __forceinline__ int scene_of_slot(const ParticleStore& S, uint32_t slot, const MaterialParams& P) {
+    if constexpr (D == 2) {
+        if (P.scenes > 1) return (int) P.scene_of[S.id[slot]];
+    }
+    return 0;
+}
+__device__ __forceinline__ MaterialParams scene_params(const MaterialParams& P, int scene) {
+    MaterialParams Q = P;
+    if (P.scenes > 1) {
+        const float2 l = __ldg(P.lame + scene);
+        Q.mu_0 = l.x, Q.lambda_0 = l.y;
+    }
+    return Q;
 }
 
 // ---- K0a: cell keys from current positions -------------------------------------------------
@@ -216,15 +237,19 @@ __global__ void __launch_bounds__(256) k_cell_keys(ParticleStore S, uint32_t n, 
         if (base_out) base_out[(size_t) i * D + d] = b[d];
         if (!s.ok) bad = true;  // stencil left [0,res] (Q5) or x is not finite
     }
+    const int xoff = scene_of_slot<D>(S, i, P) * P.n1;
     if (bad) {
         atomicOr(error_flag, 1);
         keys[i] = kKeyOutOfGrid;
     } else {
+        b[0] += xoff;
         keys[i] = cell_key<D>(b, tiles_per_axis);
+        b[0] -= xoff;
     }
     if (box) {  // flagged particles still scatter (to clamped nodes, see stencil_of): keep those nodes in the box
 #pragma unroll
         for (int d = 0; d < D; ++d) b[d] = min(max(b[d], 0), P.res - 2);
+        b[0] += xoff;
         box_update<D>(box, b, true);
     }
 }
@@ -243,9 +268,11 @@ __global__ void __launch_bounds__(256) k_reorder(ParticleStore src, ParticleStor
     dst.id[i] = __ldg(src.id + j);
 }
 
+// `xoff` (batch of stacked 2D scenes): node rows of the scenes before this particle's; added to base[0] AFTER the
+// in-grid test and the clamp, which are per scene
 template <int D>
 __device__ __forceinline__ bool stencil_of(const float (&x)[D], const MaterialParams& P, int (&base)[D], float (&fx)[D],
-                                           float (&w)[D][3]) {
+                                           float (&w)[D][3], int xoff = 0) {
     bool ok = true;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
@@ -258,6 +285,7 @@ __device__ __forceinline__ bool stencil_of(const float (&x)[D], const MaterialPa
             base[d] = min(max(s.base, 0), P.res - 2);  // keep every access in bounds; the step is flagged
         }
     }
+    base[0] += xoff;
     return ok;
 }
 
@@ -337,7 +365,9 @@ __device__ __forceinline__ void grid_op_node(float4* __restrict__ cell, const in
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-        if ((c[d] < 3 && vel[d] < 0.0f) || (c[d] >= n1 - 3 && vel[d] > 0.0f)) {
+        int cd = c[d];
+        if (D == 2 && d == 0 && P.scenes > 1) cd -= (cd / n1) * n1;  // stacked scenes: the walls are per scene
+        if ((cd < 3 && vel[d] < 0.0f) || (cd >= n1 - 3 && vel[d] > 0.0f)) {
 #pragma unroll
             for (int e = 0; e < D; ++e) vel[e] = 0.0f;
             m = 0.0f;
@@ -352,7 +382,7 @@ __global__ void __launch_bounds__(256) k_grid_op(float4* __restrict__ grid, cons
                                                  MaterialParams P) {
     int lo[D], c[D];
     uint32_t ext[D];
-    const uint32_t vol = box_extent<D>(box, P.n1, lo, ext);
+    const uint32_t vol = box_extent<D>(box, P.n1, lo, ext, P.scenes > 1 ? P.scenes * P.n1 : 0);
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < vol; i += stride) {
         const size_t node = box_node<D>(i, lo, ext, P.n1, c);
@@ -524,7 +554,7 @@ __device__ __forceinline__ void g2p_finish(PState<D>& p, const Mat<D>& Cn, const
                                            const ParticleStore& T, const uint32_t* __restrict__ perm, uint32_t src, uint32_t i,
                                            unsigned live, const MaterialParams& P, uint32_t* __restrict__ keys_out,
                                            int tiles_per_axis, const MigrateArgs& mig, int* __restrict__ box_partial,
-                                           const uint32_t* __restrict__ gone_keys, int local_reorder) {
+                                           const uint32_t* __restrict__ gone_keys, int local_reorder, int xoff = 0) {
     g2p_update<D, MODEL>(p, Cn, vn, P);
     // warp-uniform (kernel argument).  Slabs re-group as well: ranks are mapped onto the slots of the warp's LIVE lanes
     // (slots whose particle migrated away keep their "gone" mark and stay where they are).
@@ -538,8 +568,10 @@ __device__ __forceinline__ void g2p_finish(PState<D>& p, const Mat<D>& Cn, const
             b[d] = s.base;
             bad = bad || !s.ok;
         }
+        b[0] += xoff;  // batch of stacked 2D scenes: node rows of the scenes before this one (else 0)
         // an out-of-grid position is flagged by the next step's P2G/G2P (that is when the reference throws)
         uint32_t key = bad ? kKeyOutOfGrid : cell_key<D>(b, tiles_per_axis);
+        b[0] -= xoff;
         // Single GPU: the warp writes its 32 particles back GROUPED BY THEIR NEW CELL instead of slot by slot.  Between
         // two radix sorts the particles of a cell drift into 2-3 neighbouring cells and interleave (A B A A C B ...): P2G
         // then meets one run per fragment, and every run costs 27 lane-reductions.  Re-grouping inside the warp's own 32
@@ -603,6 +635,7 @@ __device__ __forceinline__ void g2p_finish(PState<D>& p, const Mat<D>& Cn, const
         if (keys_out) keys_out[dst] = key;
 #pragma unroll
         for (int d = 0; d < D; ++d) b[d] = min(max(b[d], 0), P.res - 2);
+        b[0] += xoff;
         // migrants stay in the sender's box: the box table of the slab protocol must cover them until they are unpacked
         box_partial_write<D>(box_partial, live, b, true, i >> 5);
     }
@@ -647,6 +680,7 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
     PState<D> p;
     int base[D];
     float fx[D], w[D][3];
+    int xoff = 0;                                       // batch of stacked 2D scenes: node-row offset of this particle's scene
     [[maybe_unused]] bool in_window = false;            // WINDOW: the CTA's node box fits the window and has landed
     [[maybe_unused]] const float4* win_node = nullptr;  // WINDOW: this particle's base node inside the window
     if constexpr (WINDOW) {
@@ -708,7 +742,8 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
         win_node = win + ((base[0] - mn[0]) * kWinPitch + (base[1] - mn[1]) * kWinZ + (base[2] - mn[2]));
     } else {
         load_for_g2p<D>(S, src, p);
-        if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
+        xoff = scene_of_slot<D>(S, src, P) * P.n1;
+        if (!stencil_of<D>(p.x, P, base, fx, w, xoff)) atomicOr(error_flag, 1);
     }
     // Gather with the stencil offsets centred on the middle node:  o = ijk - 1 in {-1,0,+1},
     //   v   = sum w g
@@ -756,7 +791,7 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
         }
     }
     g2p_finish<D, MODEL>(p, Cn, vn, S, T, perm, src, i, live, P, keys_out, tiles_per_axis, mig, box_partial, gone_keys,
-                         local_reorder);
+                         local_reorder, xoff);
 }
 
 // ---- K4, software-pipelined (3D): persistent CTAs, asynchronous particle rows and node windows ------------------------

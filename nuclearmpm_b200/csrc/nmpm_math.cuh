@@ -400,8 +400,17 @@ struct HCol {
         }                                                                                           \
     }
 
-template <int MODE>
-NMPM_HD bool svd3_recompose(const Mat<3>& A, float lo, float hi, Mat<3>& G) {
+// What the snow projection knows besides the projected matrix G = sum_j f_j u_j v_j^T: the clamped singular values and
+// the RIGHT singular vectors v_j of the input.  (snow_project runs on the transpose, where they are the LEFT singular
+// vectors l_j of the projected F — all the fused G2P+P2G kernel needs for the stress of the new state: with
+// F = sum f_j l_j r_j^T and R = sum l_j r_j^T,  (F - R) F^T = sum (f_j - 1) f_j l_j l_j^T  and  det F = f_0 f_1 f_2.)
+struct SvdFactors {
+    float f[3];
+    float v[3][3];  // v[j] = j-th right singular vector of the input
+};
+
+template <int MODE, bool FACTORS = false>
+NMPM_HD bool svd3_recompose(const Mat<3>& A, float lo, float hi, Mat<3>& G, SvdFactors* sf = nullptr) {
     // |a_p . a_q| <= 4 eps |a_p| |a_q| counts as orthogonal
     constexpr float kTol2 = (4.0f * FLT_EPSILON) * (4.0f * FLT_EPSILON);
     // a sweep whose largest relative inner product was below 2e-4 leaves all of them below ~4e-8 (cyclic Jacobi
@@ -474,6 +483,11 @@ NMPM_HD bool svd3_recompose(const Mat<3>& A, float lo, float hi, Mat<3>& G) {
             for (int e = 0; e < 3; ++e) uj[e] = ck[e];
         }
         const float f = (MODE == 0) ? 1.0f : clampf(sg, lo, hi);
+        if constexpr (FACTORS) {
+            sf->f[j] = f;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) sf->v[j][e] = v[j][e];
+        }
         fu01[j] = f2_mul(f2(f, f), f2(uj[0], uj[1]));
         fu2[j] = f * uj[2];
     }
@@ -571,6 +585,24 @@ NMPM_HD Mat<3> snow_project(const Mat<3>& m, float lo, float hi) {
     }
     return mat_mul_bt<3>(U, V);
 }
+// snow_project that also hands out the factors of the projected matrix (false: the fast path did not apply, `sf` is
+// not filled and the caller must decompose G itself)
+NMPM_HD bool snow_project_factors(const Mat<3>& m, float lo, float hi, Mat<3>& G, SvdFactors& sf) {
+    Mat<3> mt, Gt;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) mt(i, j) = m(j, i);
+    if (svd3_recompose<1, true>(mt, lo, hi, Gt, &sf)) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) G(i, j) = Gt(j, i);
+        return true;
+    }
+    G = snow_project(m, lo, hi);
+    return false;
+}
 NMPM_HD Mat<2> snow_project(const Mat<2>& m, float lo, float hi) {
     Mat<2> U, V;
     float sig[2];
@@ -591,6 +623,12 @@ struct MaterialParams {
     float vmax;       // (float)(dx*0.9/dt)          (src/nclr.h:285)
     float dt_gravity; // dt*gravity                  (src/nclr.h:292)
     int res, n1;      // n1 = res+1 nodes per axis
+    // Batch of independent 2D scenes advanced by the same launches (nmpm_create_batch; BASELINE config 5): the scenes'
+    // grids are stacked along x (the slowest index), scene s owns node rows [s*n1, (s+1)*n1); a particle's scene comes
+    // from its input index, and the Lame parameters are per scene.  scenes <= 1: a single scene, the pointers are unused.
+    int scenes;
+    const unsigned short* scene_of;  // scene of input index i (device)
+    const float2* lame;              // {mu_0, lambda_0} of scene s (device)
 };
 
 // hardening (src/nclr.h:351-372).  The reference evaluates the snow factor exp(10(1-Jp)) in double and
@@ -629,6 +667,35 @@ NMPM_HD Mat<D> affine_matrix(const Mat<D>& F, const Mat<D>& C, float Jp, float m
     Mat<D> A;
 #pragma unroll
     for (int k = 0; k < D * D; ++k) A.m[k] = fmaf(neg, P.Dinv * (PF.m[k] + cst), mass * C.m[k]);
+    return A;
+}
+
+// The same matrix for snow from the factors of F that the plasticity projection of the same G2P produced (see
+// SvdFactors): PF = sum_j 2mu (f_j - 1) f_j l_j l_j^T + lambda (J - 1) J ones,  J = f_0 f_1 f_2 — no polar decomposition.
+// f_j in [0.975, 1.0045] > 0, so R = sum l_j r_j^T is the rotation factor of F and det F = prod f_j (det U = det V = +1).
+NMPM_HD Mat<3> affine_matrix_snow_factors(const SvdFactors& sf, const Mat<3>& C, float Jp, float mass, float volume,
+                                          const MaterialParams& P) {
+    const float e = hardening_e<0>(Jp);
+    const float mu = P.mu_0 * e, lambda = P.lambda_0 * e;
+    const float J = sf.f[0] * sf.f[1] * sf.f[2];
+    const float cst = lambda * (J - 1.0f) * J;
+    const float two_mu = 2.0f * mu;
+    float g[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) g[j] = two_mu * (sf.f[j] - 1.0f) * sf.f[j];
+    const float neg = -(P.dt * volume) * P.Dinv;
+    Mat<3> A;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = r; c < 3; ++c) {
+            float pf = g[0] * sf.v[0][r] * sf.v[0][c];
+            pf = fmaf(g[1] * sf.v[1][r], sf.v[1][c], pf);
+            pf = fmaf(g[2] * sf.v[2][r], sf.v[2][c], pf);
+            const float t = neg * (pf + cst);
+            A(r, c) = fmaf(mass, C(r, c), t);
+            if (c != r) A(c, r) = fmaf(mass, C(c, r), t);
+        }
     return A;
 }
 

@@ -84,11 +84,13 @@ __global__ void __launch_bounds__(kP2GWarps * 32, NMPM_P2G_MINB) k_p2g_cell(Part
         if (lane < cnt && !gone) {
             PState<D> p;
             // `perm` (nullable): the store is read THROUGH the sorted permutation, no reorder pass
-            load_for_p2g<D>(S, perm ? __ldg(perm + first + lane) : first + lane, p);
+            const uint32_t src = perm ? __ldg(perm + first + lane) : first + lane;
+            load_for_p2g<D>(S, src, p);
             int base[D];
             float fx[D];
-            if (!stencil_of<D>(p.x, P, base, fx, w)) atomicOr(error_flag, 1);
-            const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, p.mass, p.volume, P);
+            const int scene = scene_of_slot<D>(S, src, P);  // batch of stacked 2D scenes (else 0)
+            if (!stencil_of<D>(p.x, P, base, fx, w, scene * P.n1)) atomicOr(error_flag, 1);
+            const Mat<D> A = affine_matrix<D, MODEL>(p.F, p.C, p.Jp, p.mass, p.volume, (D == 2) ? scene_params(P, scene) : P);
 #pragma unroll
             for (int r = 0; r < D; ++r) {
                 float afx = A(r, 0) * fx[0];

@@ -46,6 +46,29 @@ def test_teacher_forced_with_speculation_discarded_every_step(model, sort_every)
         gpu.upload(*[ref[k] for k in FIELDS])
 
 
+@pytest.mark.parametrize("model", MODELS)
+def test_scatter_ahead_against_the_oracle_one_step(model):
+    """The P2G scattered ahead by the fused kernel (for snow: stress from the SVD factors of the plasticity projection
+    instead of a polar decomposition of the stored F) against the oracle's p2g() of the same step, teacher-forced: upload
+    the oracle's state k, advance one step (stand-alone P2G of step k+1, fused G2P scatters step k+2), then read the
+    post-P2G grid of step k+2 on both sides."""
+    x, v = scene(350 + model)
+    cpu = co.CpuSim(x, model, 32, v=v)
+    gpu = nm.MPMSimulation(x, model, 32, v=v, fuse=ALWAYS)
+    for step in range(8):
+        cpu.advance(1), gpu.advance(1)
+        check_state(gpu.particles(), cpu.particles(), f"step {step + 1}")
+        ref = cpu.particles()                        # the oracle's p2g() from the oracle's own state
+        twin = co.CpuSim(ref["x"], model, 32, v=ref["v"], F=ref["F"], Cm=ref["C"], Jp=ref["Jp"])
+        twin.phase(0)
+        gpu.phase(0)
+        gv, gm = gpu.grid()
+        # the GPU scatters ITS state of step k+1 (one-step error: F to 2e-5, amplified by dt*vol*Dinv*2mu ~ 5 in the
+        # stress): twice the one-step grid tolerance
+        check_grid(gv, gm, *twin.grid(), f"P2G scattered ahead, step {step + 2}", scale=2.0)
+        gpu.upload(*[ref[k] for k in FIELDS])        # discards nothing (the P2G phase consumed it), restarts the step
+
+
 @pytest.mark.parametrize("model", [co.JELLY, co.LIQUID])
 @pytest.mark.parametrize("sort_every", [1, 4])
 def test_free_running_fused_against_oracle_and_unfused(model, sort_every):

@@ -464,7 +464,7 @@ def test_g2p_tma_window_matches_global_gather(model):
     }
     for name, x in scenes.items():
         v = rng.normal(0, 2, x.shape).astype(np.float32)
-        a = nm.MPMSimulation(x, model, 64, v=v, g2p_window=1)
+        a = nm.MPMSimulation(x, model, 64, v=v, g2p_window=1, fuse=1)   # the gather under test, not the fused scatter
         b = nm.MPMSimulation(x, model, 64, v=v, g2p_window=2)   # one-shot CTAs, TMA-staged window
         c = nm.MPMSimulation(x, model, 64, v=v, g2p_window=3)   # persistent CTAs, cp.async rows + TMA window, pipelined
         for step in range(6):

@@ -14,6 +14,8 @@ quickoff) timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --fuse 1 > 
 abminb)  for mb in 5 8; do NMPM_FUSED_MINB=$mb timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --late-step 0 > $out/bench_minb$mb.json 2> $out/bench_minb$mb.err; echo "minb $mb rc=$?"; python tools/bench_summary.py $out/bench_minb$mb.json; done;;
 ncufused) timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_g2p_p2g' -s 28 -c 4 \
             -f -o $out/prof_cfg4_fused python tools/profile_step.py --workload cfg4 --warmup 28 --steps 6 --sort-every 4 > $out/ncu_fused.log 2>&1; echo "ncu rc=$?"; tail -2 $out/ncu_fused.log;;
+abflags) for cfg in "0 6 4" "2 6 4" "4 6 4" "6 6 4" "6 8 4" "6 6 2" "6 6 3" "6 8 2"; do set -- $cfg; NMPM_FUSED_FLAGS=$1 NMPM_FUSED_MINB=$2 timeout 600 python bench.py --steps 24 --warmup 5 --no-cpu --late-step 0 --sort-every $3 > $out/bench_f$1_b$2_s$3.json 2> $out/bench_f$1_b$2_s$3.err; echo "flags $1 minb $2 sort $3 rc=$?"; python tools/bench_summary.py $out/bench_f$1_b$2_s$3.json; done;;
+occupancy) timeout 900 python tools/grid_occupancy.py --workload cfg4 --steps 40 150 300 > $out/grid_occupancy.jsonl 2> $out/grid_occupancy.err; echo "occupancy rc=$?"; cat $out/grid_occupancy.jsonl;;
 smoke)   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $out/smoke.log;;
 bench)   timeout 900 python bench.py --steps 20 --warmup 5 > $out/bench_default.json 2> $out/bench_default.err; echo "bench rc=$?"; tail -3 $out/bench_default.err; python tools/bench_summary.py $out/bench_default.json;;
 quick)   timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu > $out/bench_quick.json 2> $out/bench_quick.err; echo "bench rc=$?"; tail -3 $out/bench_quick.err; python tools/bench_summary.py $out/bench_quick.json;;

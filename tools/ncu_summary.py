@@ -33,7 +33,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("raw")
 ap.add_argument("--title", default="")
 ap.add_argument("--particles", type=float, default=0)
-ap.add_argument("--algo", default="p2g=108,g2p=152")
+ap.add_argument("--algo", default="p2g=108,g2p=152,g2p_p2g=260")
 a = ap.parse_args()
 algo = {k: float(v) for k, v in (kv.split("=") for kv in a.algo.split(","))}
 
@@ -73,7 +73,9 @@ for label, key, want in ROWS:
 if a.particles:
     ab, ratio, wi = [], [], []
     for n, r in zip(names, data):
-        k = "p2g" if "p2g" in n else "g2p" if "g2p" in n else None
+        k = "g2p_p2g" if "g2p_p2g" in n else "p2g" if "p2g" in n else "g2p" if "g2p" in n else None
+        if k not in algo:
+            k = None
         tr = (val(r, "dram__bytes_read.sum", "MB") or 0) + (val(r, "dram__bytes_write.sum", "MB") or 0)
         if k:
             b = algo[k] * a.particles / 1e6
