@@ -64,7 +64,12 @@ struct nmpm_sim {
     int fuse = 0;            // 0 off, 1 on (not on the first step after an upload: that state may be replaced again), 2 always
     bool p2g_ahead = false;  // grid_alt holds the P2G of store[cur] (the coming step) over box[box_cur]
     int grid_sel = 0;        // which of the two buffers `grid` is (CUDA-graph key)
-    int fused_minb = NMPM_FUSED_MINB;  // CTAs per SM the fused kernel is compiled for (env NMPM_FUSED_MINB: experiments)
+    int fused_minb = NMPM_FUSED_MINB;
+    // active node tiles (nmpm_kernels.cuh: k_tiles3; 3D, single GPU): one flag bit per 4^3-node tile, raised for the
+    // NEXT step's stencils by whoever produces the positions (G2P, the key pass), consumed by grid_op and the clear (NMPM_TILES=0: node boxes as in 2D / slabs)
+    // Ring like the node boxes and indexed like them: tile_ring[b] belongs to the positions box[b] bounds.
+    uint32_t* tile_ring[kBoxRing] = {nullptr, nullptr, nullptr, nullptr};
+    bool tiles = false;  // CTAs per SM the fused kernel is compiled for (env NMPM_FUSED_MINB: experiments)
     // node boxes (GridBox, device): box[box_cur] bounds the particles of the current step, box[(box_cur+3)%4]
     // the nodes the previous P2G wrote (cleared at the start of the next one), box[(box_cur+1)%4] is being
     // built by the G2P in flight
@@ -347,6 +352,17 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
             CUDA_TRY(h, cudaMemset(h->grid_alt, 0, h->cells * sizeof(float4)));
         }
     }
+    if (dim == 3 && !h->slab) {
+        const char* tl = std::getenv("NMPM_TILES");
+        if (!tl || *tl != '0') {
+            const size_t T = (n1 + 3) / 4, bytes = ((T * T * T + 31) / 32 + 16) * sizeof(uint32_t);
+            for (int k = 0; k < kBoxRing; ++k) {
+                CUDA_TRY(h, cudaMalloc(&h->tile_ring[k], bytes));
+                CUDA_TRY(h, cudaMemset(h->tile_ring[k], 0, bytes));
+            }
+            h->tiles = true;
+        }
+    }
     CUDA_TRY(h, cudaMalloc(&h->d_box, kBoxRing * sizeof(GridBox)));
     CUDA_TRY(h, cudaMalloc(&h->d_box_partial, ((h->cap + 127) / 128 * 4 + 4) * 8 * sizeof(int)));
     for (int k = 0; k < kBoxRing; ++k) k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + k);
@@ -406,6 +422,8 @@ void nmpm_destroy(nmpm_handle h) {
     free_store(h->store[1]);
     if (h->grid) cudaFree(h->grid);
     if (h->grid_alt) cudaFree(h->grid_alt);
+    for (auto* t : h->tile_ring)
+        if (t) cudaFree(t);
     if (h->d_box) cudaFree(h->d_box);
     if (h->d_box_partial) cudaFree(h->d_box_partial);
     if (h->d_error) cudaFree(h->d_error);
@@ -587,7 +605,7 @@ static int do_sort(nmpm_sim* h) {
         k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + h->box_cur);
         NMPM_DISPATCH_DIM(h, (k_cell_keys<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(
                                  S, n, h->P, h->tiles_per_axis, h->sort.keys_a, nullptr, h->d_error,
-                                 h->d_box + h->box_cur)));
+                                 h->d_box + h->box_cur, h->tiles ? h->tile_ring[h->box_cur] : nullptr)));
         h->launches += 2;
         h->box_valid = true;
     }
@@ -620,18 +638,28 @@ static int ensure_box(nmpm_sim* h) {
     k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + h->box_cur);
     NMPM_DISPATCH_DIM(h, (k_cell_keys<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(
                              h->store[h->cur], n, h->P, h->tiles_per_axis, h->sort.keys_b, nullptr, h->d_error,
-                             h->d_box + h->box_cur)));
+                             h->d_box + h->box_cur, h->tiles ? h->tile_ring[h->box_cur] : nullptr)));
     h->launches += 2;
     h->box_valid = true;
     return NMPM_OK;
+}
+
+// zero what the P2G of the positions of box `box` scattered into `grid`: their flagged tiles (lowering the flags), or the
+// node box itself
+static void clear_grid(nmpm_sim* h, float4* grid, int box) {
+    if (h->tiles) {
+        k_tiles3<0><<<kBoxBlocks, 256, 0, h->stream>>>(grid, h->tile_ring[box], h->P);
+    } else {
+        NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(grid, h->d_box + box, h->P.n1)));
+    }
+    h->launches++;
 }
 
 // The particle state is about to be replaced (upload): the sums the last fused G2P scattered ahead into grid_alt belong to
 // the old state.  They cover box[box_cur]; zero them (before the key pass of the new state resets that box).
 static void discard_p2g_ahead(nmpm_sim* h) {
     if (!h->p2g_ahead) return;
-    NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid_alt, h->d_box + h->box_cur, h->P.n1)));
-    h->launches++;
+    clear_grid(h, h->grid_alt, h->box_cur);
     h->p2g_ahead = false;
 }
 
@@ -643,17 +671,14 @@ static int do_p2g(nmpm_sim* h) {
         h->grid_sel ^= 1;
         h->p2g_ahead = false;
         k_promote_error<<<1, 32, 0, h->stream>>>(h->d_error);
-        NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(
-                                 h->grid_alt, h->d_box + (h->box_cur + kBoxRing - 1) % kBoxRing, h->P.n1)));
-        h->launches += 2;
+        h->launches++;
+        clear_grid(h, h->grid_alt, (h->box_cur + kBoxRing - 1) % kBoxRing);
         h->grid_valid = true;
         return NMPM_OK;
     }
     if (int rc = ensure_box(h)) return rc;
     // K1: clear what the previous P2G (and, for a slab, the neighbours' ghost planes) wrote
-    NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + (h->box_cur + kBoxRing - 1) % kBoxRing,
-                                                                            h->P.n1)));
-    h->launches++;
+    clear_grid(h, h->grid, (h->box_cur + kBoxRing - 1) % kBoxRing);
     for (const auto& pr : h->dirty_planes)
         CUDA_TRY(h, cudaMemsetAsync(nmpm_grid_plane_ptr(h, pr.first), 0, (size_t) pr.second * nmpm_grid_plane_bytes(h),
                                     h->stream));
@@ -693,7 +718,11 @@ static int do_p2g(nmpm_sim* h) {
 }
 
 static int do_grid_op(nmpm_sim* h) {
-    NMPM_DISPATCH_DIM(h, (k_grid_op<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + h->box_cur, h->P)));
+    if (h->tiles) {
+        k_tiles3<1><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->tile_ring[h->box_cur], h->P);
+    } else {
+        NMPM_DISPATCH_DIM(h, (k_grid_op<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + h->box_cur, h->P)));
+    }
     h->launches++;
     return NMPM_OK;
 }
@@ -717,50 +746,51 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
     uint32_t* keys_out = (next_sorts || h->slab) ? h->sort.keys_a : nullptr;
     const uint32_t* gone_keys = (h->dev_counts || (h->slab && !h->perm && h->n_gone)) ? h->sort.keys_a : nullptr;
     const int box_next = (h->box_cur + 1) % kBoxRing;
+    uint32_t* tiles_next = h->tiles ? h->tile_ring[box_next] : nullptr;  // active node tiles of the coming step
     k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + box_next);
     // fused G2P+P2G: not on the first step after an upload (fuse == 1) — that state is likely to be replaced again
     const bool fused = h->fuse && !mig.left && (h->fuse == 2 || h->steps_done > 0);
     if (fused) {
         if (h->model == 0)
             launch_g2p_p2g<0>(S, T, h->perm, n, h->P, h->grid, h->grid_alt, keys_out, h->tiles_per_axis, h->d_error,
-                              h->d_box_partial, h->local_reorder ? 1 : 0, h->stream, h->fused_minb);
+                              h->d_box_partial, h->local_reorder ? 1 : 0, tiles_next, h->stream, h->fused_minb);
         else if (h->model == 1)
             launch_g2p_p2g<1>(S, T, h->perm, n, h->P, h->grid, h->grid_alt, keys_out, h->tiles_per_axis, h->d_error,
-                              h->d_box_partial, h->local_reorder ? 1 : 0, h->stream, h->fused_minb);
+                              h->d_box_partial, h->local_reorder ? 1 : 0, tiles_next, h->stream, h->fused_minb);
         else
             launch_g2p_p2g<2>(S, T, h->perm, n, h->P, h->grid, h->grid_alt, keys_out, h->tiles_per_axis, h->d_error,
-                              h->d_box_partial, h->local_reorder ? 1 : 0, h->stream, h->fused_minb);
+                              h->d_box_partial, h->local_reorder ? 1 : 0, tiles_next, h->stream, h->fused_minb);
         h->p2g_ahead = true;
     } else if (h->g2p_window && h->g2p_pipe) {  // 3D only: persistent CTAs, pipelined rows (cp.async) and node windows (TMA)
         const unsigned chunks = blocks_for(n, 128);
         const unsigned grid_ctas = chunks < (unsigned) (148 * NMPM_G2P_PIPE_MINB) ? chunks : (unsigned) (148 * NMPM_G2P_PIPE_MINB);
         if (h->model == 0)
             k_g2p_pipe<0><<<grid_ctas, 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error,
-                                                            mig, h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
+                                                            mig, h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map, tiles_next);
         else if (h->model == 1)
             k_g2p_pipe<1><<<grid_ctas, 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error,
-                                                            mig, h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
+                                                            mig, h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map, tiles_next);
         else
             k_g2p_pipe<2><<<grid_ctas, 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error,
-                                                            mig, h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
+                                                            mig, h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map, tiles_next);
     } else if (h->g2p_window) {  // 3D only (set at creation): one-shot CTAs with a TMA-staged node window
         constexpr int D = 3;
         if (h->model == 0)
             k_g2p_gather<D, 0, true><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out,
                                                                                h->tiles_per_axis, h->d_error, mig, h->d_box_partial,
-                                                                               gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
+                                                                               gone_keys, h->local_reorder ? 1 : 0, h->grid_map, tiles_next);
         else if (h->model == 1)
             k_g2p_gather<D, 1, true><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out,
                                                                                h->tiles_per_axis, h->d_error, mig, h->d_box_partial,
-                                                                               gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
+                                                                               gone_keys, h->local_reorder ? 1 : 0, h->grid_map, tiles_next);
         else
             k_g2p_gather<D, 2, true><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out,
                                                                                h->tiles_per_axis, h->d_error, mig, h->d_box_partial,
-                                                                               gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
+                                                                               gone_keys, h->local_reorder ? 1 : 0, h->grid_map, tiles_next);
     } else {
         NMPM_DISPATCH(h, (k_g2p_gather<D, MODEL, false><<<blocks_for(n, 128), 128, 0, h->stream>>>(
                              S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error, mig,
-                             h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map)));
+                             h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map, tiles_next)));
     }
     {   // warps of the launch above (128-thread CTAs): every one of them wrote a partial box
         const uint32_t nwarps = blocks_for(n, 128) * 4u - ((blocks_for(n, 128) * 128u - n) / 32u);
@@ -1094,8 +1124,7 @@ int nmpm_upload_particles(nmpm_handle h, const float* x, const float* v, const f
         // written the nodes of box[box_cur], and the next step only clears box[box_cur-1] (which that P2G cleared
         // itself) before the key pass rebuilds box[box_cur].  Zero those nodes now, or later steps would accumulate on
         // top of the stale sums.
-        NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + h->box_cur, h->P.n1)));
-        h->launches++;
+        clear_grid(h, h->grid, h->box_cur);
     }
     // slots go back to input order: carry mass/volume over through id
     NMPM_DISPATCH_DIM(h, (k_restore_constants<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(S, T, (uint32_t) n)));
@@ -1168,10 +1197,7 @@ int nmpm_upload_particles_async(nmpm_handle h, const float* x, const float* v, c
     ParticleStore& S = h->store[h->cur];
     ParticleStore& T = h->store[h->cur ^ 1];
     discard_p2g_ahead(h);
-    if (h->phase_next != 0) {  // see nmpm_upload_particles
-        NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + h->box_cur, h->P.n1)));
-        h->launches++;
-    }
+    if (h->phase_next != 0) clear_grid(h, h->grid, h->box_cur);  // see nmpm_upload_particles
     NMPM_DISPATCH_DIM(h, (k_restore_constants<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(S, T, (uint32_t) n)));
     NMPM_DISPATCH_DIM(h, (k_import_soa<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(dx, dv, dF, dC, dJ, nullptr, nullptr,
                                                                                      (uint32_t) n, T, 1)));

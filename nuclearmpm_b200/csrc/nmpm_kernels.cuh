@@ -201,6 +201,120 @@ __global__ void __launch_bounds__(256) k_clear_box(float4* __restrict__ grid, co
         grid[box_node<D>(i, lo, ext, n1, c)] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
+// ---- active node tiles (3D, single GPU) --------------------------------------------------------------------------
+// The node box above is exact for a compact block, but the 3D snow scenes turn into thin sheets and droplets that fill
+// their bounding box very sparsely (cfg4 at step 300: the box holds 95 M nodes, 9 M of them non-zero, tools/
+// grid_occupancy.py) while clear + grid_op stream over all of it.  Tile mode: the dense grid is cut into tiles of
+// 4^3 nodes with one flag bit each; the flags of the tiles the stencils cover are raised together with the node box,
+// grid_op and the clear visit only flagged tiles (the clear also lowers the flags).  The flag array of the whole 513^3
+// grid is 268 KB, so it is simply scanned in full: no compaction, no box.
+// A stencil with base b covers nodes b..b+2 per axis, i.e. the tile of b and, where (b & 3) >= 2, the next one.
+struct TileMark {
+    uint32_t lo;   // tile of the base node (linear, x slowest)
+    int straddle;  // bit 0/1/2: the stencil reaches into the next tile along x/y/z
+};
+__device__ __forceinline__ int node_tiles_per_axis(int n1) { return (n1 + 3) >> 2; }
+__device__ __forceinline__ TileMark tile_mark3(const int (&b)[3], int T) {
+    TileMark m;
+    m.lo = (uint32_t) (((b[0] >> 2) * T + (b[1] >> 2)) * T + (b[2] >> 2));
+    m.straddle = ((b[0] & 3) >= 2 ? 1 : 0) | ((b[1] & 3) >= 2 ? 2 : 0) | ((b[2] & 3) >= 2 ? 4 : 0);
+    return m;
+}
+// Raised by whoever produces the next step's positions (G2P, the key pass) — like the node box, and at the same places —
+// once per WARP and distinct tile, not per particle or per run: the lanes of a warp whose stencils start in the same tile
+// (__match_any_sync; 32 cell-sorted particles sit in 1-3 tiles) OR their corner sets together and their first lane does
+// the work.  The flags are BITS (32 tiles per word) raised with a 32-bit reduction (RED.OR at the L2) after a test through
+// L1: a flag only goes 0 -> 1 while the kernel runs, so a stale 0 costs one redundant reduction and nothing else.
+// Measured on cfg4 (gpurun r2u-r2y): one flag BYTE per tile raised with plain stores costs +0.4 ms per step — 4 M one-byte
+// partial-sector writes; every other store of the step fills whole 32-byte sectors — and raising them from the P2G
+// kernels' run flushes instead +0.3 ms.  All loads are issued before the first reduction.  Called by the lanes of `live`.
+__device__ __forceinline__ void tile_mark_warp(uint32_t* flags, unsigned live, const int (&b)[3], int T) {
+    const TileMark m = tile_mark3(b, T);
+    unsigned cm = 1u;  // bit c: corner tile c = (c&1 ? +x) (c&2 ? +y) (c&4 ? +z) is covered by this lane's stencil
+    if (m.straddle & 1) cm |= cm << 1;
+    if (m.straddle & 2) cm |= cm << 2;
+    if (m.straddle & 4) cm |= cm << 4;
+    const unsigned peers = __match_any_sync(live, m.lo);
+    const unsigned um = __reduce_or_sync(peers, cm);
+    if ((int) (threadIdx.x & 31) != __ffs(peers) - 1) return;
+    unsigned set = 0u;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        if ((um >> c) & 1u) {
+            const uint32_t t = m.lo + (uint32_t) (((c & 1) ? T * T : 0) + ((c & 2) ? T : 0) + ((c & 4) ? 1 : 0));
+            set |= ((__ldca(flags + (t >> 5)) >> (t & 31u)) & 1u) << c;
+        }
+    const unsigned todo = um & ~set;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        if ((todo >> c) & 1u) {
+            const uint32_t t = m.lo + (uint32_t) (((c & 1) ? T * T : 0) + ((c & 2) ? T : 0) + ((c & 4) ? 1 : 0));
+            atomicOr(flags + (t >> 5), 1u << (t & 31u));
+        }
+}
+
+// One warp per flag word (32 consecutive tiles): the warp visits every flagged tile — lane -> (row, half): 16 (x,y) rows
+// of 4 z-contiguous nodes, two nodes (32 B) per lane.  OP 0: zero the nodes and lower the flags; OP 1: grid_op.
+template <int D>
+__device__ __forceinline__ bool grid_op_value(float4& g, const int (&c)[D], const MaterialParams& P);
+template <int OP>
+__global__ void __launch_bounds__(256) k_tiles3(float4* __restrict__ grid, uint32_t* __restrict__ flags, MaterialParams P) {
+    constexpr int U = 4;  // flagged tiles in flight per warp (their loads are issued together)
+    const int n1 = P.n1, T = node_tiles_per_axis(n1);
+    const uint32_t nwords = ((uint32_t) (T * T * T) + 31u) >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int row = lane & 15, half = lane >> 4;
+    for (uint32_t w = warp; w < nwords; w += nwarps) {
+        unsigned active = flags[w];
+        if (active == 0u) continue;
+        if (OP == 0 && lane == 0) flags[w] = 0u;
+        const uint32_t t0 = w << 5;
+        while (active) {
+            float4* node[U];
+            int c[U][3];
+            bool ok[U][2];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                node[u] = nullptr;
+                ok[u][0] = ok[u][1] = false;
+                if (active) {
+                    const uint32_t t = t0 + (uint32_t) (__ffs(active) - 1);
+                    active &= active - 1u;
+                    const uint32_t q = t / (uint32_t) T;
+                    const int tz = (int) (t - q * (uint32_t) T), ty = (int) (q % (uint32_t) T), tx = (int) (q / (uint32_t) T);
+                    c[u][0] = 4 * tx + (row >> 2), c[u][1] = 4 * ty + (row & 3), c[u][2] = 4 * tz + 2 * half;
+                    if (c[u][0] < n1 && c[u][1] < n1) {
+                        node[u] = grid + ((size_t) (c[u][0] * n1 + c[u][1]) * n1 + c[u][2]);
+                        ok[u][0] = c[u][2] < n1, ok[u][1] = c[u][2] + 1 < n1;
+                    }
+                }
+            }
+            if constexpr (OP == 0) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        if (ok[u][e]) node[u][e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            } else {
+                float4 g[U][2];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) g[u][e] = ok[u][e] ? node[u][e] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if (!ok[u][e]) continue;
+                        const int cc[3] = {c[u][0], c[u][1], c[u][2] + e};
+                        if (grid_op_value<3>(g[u][e], cc, P)) node[u][e] = g[u][e];
+                    }
+            }
+        }
+    }
+}
+
 // Batch of stacked 2D scenes (MaterialParams::scenes): scene of the particle in slot `slot`, and the node-row offset
 // that turns its base.x into the stacked grid's.  Single scene / 3D: 0.
 template <int D>
@@ -223,7 +337,8 @@ __device__ __forceinline__ MaterialParams scene_params(const MaterialParams& P, 
 template <int D>
 __global__ void __launch_bounds__(256) k_cell_keys(ParticleStore S, uint32_t n, MaterialParams P, int tiles_per_axis,
                                                    uint32_t* __restrict__ keys, int32_t* __restrict__ base_out,
-                                                   int* __restrict__ error_flag, GridBox* __restrict__ box) {
+                                                   int* __restrict__ error_flag, GridBox* __restrict__ box,
+                                                   uint32_t* tile_flags = nullptr) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float x[D];
@@ -251,6 +366,9 @@ __global__ void __launch_bounds__(256) k_cell_keys(ParticleStore S, uint32_t n, 
         for (int d = 0; d < D; ++d) b[d] = min(max(b[d], 0), P.res - 2);
         b[0] += xoff;
         box_update<D>(box, b, true);
+        if constexpr (D == 3) {
+            if (tile_flags) tile_mark_warp(tile_flags, __activemask(), b, node_tiles_per_axis(P.n1));
+        }
     }
 }
 
@@ -342,12 +460,12 @@ __global__ void __launch_bounds__(128) k_p2g_scatter(ParticleStore S, const uint
 // ---- K3: grid update (src/nclr.h:263-310) ---------------------------------------------------
 // One thread per node, float4 in / float4 out.  Normalise by mass, gravity on y (Q7), clamp to
 // ±0.9 dx/dt, then the sticky 3-node walls which zero the WHOLE node incl. its mass (Q6).
+// the update of one node value; false: the node stays as it is (nothing to write)
 template <int D>
-__device__ __forceinline__ void grid_op_node(float4* __restrict__ cell, const int (&c)[D], const MaterialParams& P) {
-    float4 g = *cell;
+__device__ __forceinline__ bool grid_op_value(float4& g, const int (&c)[D], const MaterialParams& P) {
     // untouched node (all zero): normalisation is skipped (mass == 0) and the sticky walls only act on
     // non-zero velocities, so the node stays as it is
-    if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && g.w == 0.0f) return;
+    if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && g.w == 0.0f) return false;
     float vel[D];
     float m;
     if constexpr (D == 3) {
@@ -373,7 +491,13 @@ __device__ __forceinline__ void grid_op_node(float4* __restrict__ cell, const in
             m = 0.0f;
         }
     }
-    *cell = node_pack<D>(vel, m);
+    g = node_pack<D>(vel, m);
+    return true;
+}
+template <int D>
+__device__ __forceinline__ void grid_op_node(float4* __restrict__ cell, const int (&c)[D], const MaterialParams& P) {
+    float4 g = *cell;
+    if (grid_op_value<D>(g, c, P)) *cell = g;
 }
 
 // grid-stride over the node box of the current particles (see GridBox)
@@ -554,7 +678,8 @@ __device__ __forceinline__ void g2p_finish(PState<D>& p, const Mat<D>& Cn, const
                                            const ParticleStore& T, const uint32_t* __restrict__ perm, uint32_t src, uint32_t i,
                                            unsigned live, const MaterialParams& P, uint32_t* __restrict__ keys_out,
                                            int tiles_per_axis, const MigrateArgs& mig, int* __restrict__ box_partial,
-                                           const uint32_t* __restrict__ gone_keys, int local_reorder, int xoff = 0) {
+                                           const uint32_t* __restrict__ gone_keys, int local_reorder, int xoff = 0,
+                                           uint32_t* tile_flags_next = nullptr) {
     g2p_update<D, MODEL>(p, Cn, vn, P);
     // warp-uniform (kernel argument).  Slabs re-group as well: ranks are mapped onto the slots of the warp's LIVE lanes
     // (slots whose particle migrated away keep their "gone" mark and stay where they are).
@@ -638,6 +763,9 @@ __device__ __forceinline__ void g2p_finish(PState<D>& p, const Mat<D>& Cn, const
         b[0] += xoff;
         // migrants stay in the sender's box: the box table of the slab protocol must cover them until they are unpacked
         box_partial_write<D>(box_partial, live, b, true, i >> 5);
+        if constexpr (D == 3) {
+            if (tile_flags_next) tile_mark_warp(tile_flags_next, live, b, node_tiles_per_axis(P.n1));
+        }
     }
 }
 
@@ -659,7 +787,8 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
                                                     uint32_t* __restrict__ keys_out, int tiles_per_axis,
                                                     int* __restrict__ error_flag, MigrateArgs mig,
                                                     int* __restrict__ box_partial, const uint32_t* __restrict__ gone_keys,
-                                                    int local_reorder, const __grid_constant__ CUtensorMap grid_map) {
+                                                    int local_reorder, const __grid_constant__ CUtensorMap grid_map,
+                                                    uint32_t* tile_flags_next = nullptr) {
     static_assert(!WINDOW || D == 3, "the TMA node window is a 3D path");
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // slab mode between sorts: a slot whose particle migrated away is skipped (its key stays kKeyGone)
@@ -791,7 +920,7 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
         }
     }
     g2p_finish<D, MODEL>(p, Cn, vn, S, T, perm, src, i, live, P, keys_out, tiles_per_axis, mig, box_partial, gone_keys,
-                         local_reorder, xoff);
+                         local_reorder, xoff, tile_flags_next);
 }
 
 // ---- K4, software-pipelined (3D): persistent CTAs, asynchronous particle rows and node windows ------------------------
@@ -816,7 +945,8 @@ __global__ void __launch_bounds__(128, NMPM_G2P_PIPE_MINB) k_g2p_pipe(ParticleSt
                                                                  uint32_t* __restrict__ keys_out, int tiles_per_axis,
                                                                  int* __restrict__ error_flag, MigrateArgs mig,
                                                                  int* __restrict__ box_partial, const uint32_t* __restrict__ gone_keys,
-                                                                 int local_reorder, const __grid_constant__ CUtensorMap grid_map) {
+                                                                 int local_reorder, const __grid_constant__ CUtensorMap grid_map,
+                                                                 uint32_t* tile_flags_next = nullptr) {
     constexpr int D = 3;
     __shared__ __align__(128) float4 win[kWinX * kWinPitch];
     __shared__ __align__(16) float4 rows[4][128];
@@ -962,7 +1092,7 @@ __global__ void __launch_bounds__(128, NMPM_G2P_PIPE_MINB) k_g2p_pipe(ParticleSt
             }
         } else if (mine) {
             g2p_finish<D, MODEL>(p, Cn, vn, S, T, perm, src, i, live, P, keys_out, tiles_per_axis, mig, box_partial, gone_keys,
-                                 local_reorder);
+                                 local_reorder, 0, tile_flags_next);
         }
     }
 }
