@@ -70,7 +70,11 @@ typedef struct nmpm_options {
                          0 = auto (on), 1 = off, 2 = on except for the first step after an upload (the uploaded state is
                          likely to be replaced again: teacher-forced loops), 3 = always.  Env NMPM_FUSE=0/1/2 (= 1/2/3)
                          overrides.  Results: same sums in a different floating-point order (like any sort cadence) */
-    int reserved[7];
+    int tiles;        /* 3D, single GPU: grid_op and the grid clear visit only the 4^3-node tiles that stencils cover (one flag
+                         bit per tile, raised together with the node box) instead of the particles' whole bounding box.
+                         0 = adaptive (on while the box holds more than ~1.5 nodes per particle, i.e. a dispersed scene),
+                         1 = never, 2 = always.  Env NMPM_TILES=0/1/2 (= never / adaptive / always) overrides.  Same results */
+    int reserved[6];
 } nmpm_options;
 
 void nmpm_default_options(nmpm_options *opt);
@@ -86,6 +90,24 @@ int nmpm_create(int dim, int model, int res, float dt, float E, float nu, float 
  * `stride` = sizeof(Particle<dim>).  The int colour `c` is kept and returned by download_aos. */
 int nmpm_create_aos(int dim, int model, int res, float dt, float E, float nu, float gravity, size_t n,
                     const void *particles_aos, size_t stride, const nmpm_options *opt, nmpm_handle *out);
+
+/* A batch of independent 2D scenes behind ONE handle, advanced by the same launches (BASELINE.json config 5: 64 two-cube
+ * scenes of 1 250 particles each; the reference runs one scene per process, src/solver.cpp:45-62,133-149 — a step of such a
+ * scene is ~14 kernels of a few microseconds, so scene-by-scene the GPU is dispatch-bound).  The scenes share model, res, dt
+ * and gravity and differ in particles and in E / nu.  Their grids are stacked along x (scene s owns node rows
+ * [s*(res+1), (s+1)*(res+1)) of one tall grid), a particle's scene follows from its input index, every per-scene rule
+ * (in-grid test, sticky walls, Lame parameters) is applied per scene: each scene evolves exactly as it would alone, up to
+ * the order of floating-point sums.  Particle arrays = the scenes' arrays concatenated (counts[s] particles each);
+ * downloads return the same layout; nmpm_download_grid* return nscenes*(res+1)^2 cells, scene by scene.
+ * An out-of-grid particle in any scene fails the whole batch (NMPM_ERR_OUT_OF_GRID). */
+int nmpm_create_batch(int model, int res, float dt, float gravity, int nscenes, const size_t *counts, const float *E,
+                      const float *nu, const float *x, const float *v, const float *F, const float *C, const float *Jp,
+                      const float *mass, const float *volume, const nmpm_options *opt, nmpm_handle *out);
+int nmpm_create_batch_aos(int model, int res, float dt, float gravity, int nscenes, const size_t *counts, const float *E,
+                          const float *nu, const void *particles_aos, size_t stride, const nmpm_options *opt,
+                          nmpm_handle *out);
+int nmpm_num_scenes(nmpm_handle h);                                   /* 1 for a plain sim */
+int nmpm_batch_lame(nmpm_handle h, float *mu_0, float *lambda_0);     /* per scene (src/nclr.h:76-77), nscenes each */
 
 void nmpm_destroy(nmpm_handle h);
 
@@ -162,6 +184,8 @@ long long nmpm_launch_count(nmpm_handle h);
 /* 1 (or 2 = also right after an upload) when this sim runs the fused G2P+P2G kernel (nmpm_options.fuse), else 0: the
  * NMPM_T_G2P timer then covers G2P of step n AND the P2G scatter of step n+1, NMPM_T_P2G only the buffer swap + clear */
 int nmpm_fused(nmpm_handle h);
+/* 1 while the sim raises / uses active node tiles (nmpm_options.tiles; adaptive: follows the node box), else 0 */
+int nmpm_tiles_active(nmpm_handle h);
 
 /* Stream plumbing: run on an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream). */
 int nmpm_set_stream(nmpm_handle h, void *cuda_stream);

@@ -5,8 +5,8 @@ include/nclr.h, the drop-in C++ header.  This package is the Python mirror of th
 (reference: class MPMSimulation<dim>, src/nclr.h:63-87) used by the tests and bench.py.
 There is no CPU fallback: importing works anywhere, computing needs a B200.
 """
-from .sim import (MPMSimulation, MaterialModel, NmpmError, OutOfGridError, cube, lib_path, load_library,  # noqa: F401
+from .sim import (MPMBatch, MPMSimulation, MaterialModel, NmpmError, OutOfGridError, cube, lib_path, load_library,  # noqa: F401
                   polar_batch, snow_project_batch, svd_batch)
 
-__all__ = ["MPMSimulation", "MaterialModel", "NmpmError", "OutOfGridError", "cube", "lib_path", "load_library",
+__all__ = ["MPMBatch", "MPMSimulation", "MaterialModel", "NmpmError", "OutOfGridError", "cube", "lib_path", "load_library",
            "svd_batch", "polar_batch", "snow_project_batch"]

@@ -68,8 +68,22 @@ struct nmpm_sim {
     // active node tiles (nmpm_kernels.cuh: k_tiles3; 3D, single GPU): one flag bit per 4^3-node tile, raised for the
     // NEXT step's stencils by whoever produces the positions (G2P, the key pass), consumed by grid_op and the clear (NMPM_TILES=0: node boxes as in 2D / slabs)
     // Ring like the node boxes and indexed like them: tile_ring[b] belongs to the positions box[b] bounds.
+    // batch of independent 2D scenes stacked along x (nmpm_create_batch*): MaterialParams::scenes / scene_of / lame
+    int scenes = 1;
+    unsigned short* d_scene_of = nullptr;
+    float2* d_lame = nullptr;
+    std::vector<float2> lame_host;
     uint32_t* tile_ring[kBoxRing] = {nullptr, nullptr, nullptr, nullptr};
-    bool tiles = false;  // CTAs per SM the fused kernel is compiled for (env NMPM_FUSED_MINB: experiments)
+    bool tiles = false;      // flag arrays allocated (3D, single GPU)
+    // Tile mode is adaptive: a compact block fills its node box and the flags only cost time (+3 % of G2P), a dispersed
+    // scene (cfg4 after ~100 steps) leaves 85-90 % of the box empty.  `tile_want` follows the box volume read back
+    // without a host wait (h_boxinfo); flags are valid only for ring slots whose positions were produced while it was on.
+    int tile_policy = 0;     // nmpm_options.tiles: 0 adaptive, 1 never, 2 always
+    bool tile_want = false;
+    bool tile_valid[kBoxRing] = {false, false, false, false};
+    int* h_boxinfo = nullptr;         // pinned copy of a recent GridBox (8 ints)
+    cudaEvent_t boxinfo_ev = nullptr;
+    bool boxinfo_pending = false;  // CTAs per SM the fused kernel is compiled for (env NMPM_FUSED_MINB: experiments)
     // node boxes (GridBox, device): box[box_cur] bounds the particles of the current step, box[(box_cur+3)%4]
     // the nodes the previous P2G wrote (cleared at the start of the next one), box[(box_cur+1)%4] is being
     // built by the G2P in flight
@@ -124,6 +138,7 @@ struct nmpm_sim {
         int box_after = 0;
         bool keys_valid_after = false;
         bool ahead_after = false;
+        bool tile_valid_after[kBoxRing] = {false, false, false, false};
         int grid_sel_after = 0;
         int launches = 0;
     };
@@ -264,8 +279,21 @@ static int make_grid_map(nmpm_sim* h) {
     return r == CUDA_SUCCESS ? NMPM_OK : NMPM_ERR_CUDA;
 }
 
+// Batch of independent 2D scenes (nmpm_create_batch / nmpm_create_batch_aos)
+struct BatchSpec {
+    int nscenes;
+    const size_t* counts;  // particles per scene; the particle arrays are the scenes' concatenated
+    const float* E;
+    const float* nu;
+};
+
+static void lame_of(float E, float nu, float* mu_0, float* lambda_0) {  // src/nclr.h:76-77, in float like the reference
+    *mu_0 = E / (2 * (1 + nu));
+    *lambda_0 = E * nu / ((1 + nu) * (1 - 2 * nu));
+}
+
 static int create_common(int dim, int model, int res, float dt, float E, float nu, float gravity, size_t n,
-                         const nmpm_options* opt, nmpm_sim** out) {
+                         const nmpm_options* opt, nmpm_sim** out, const BatchSpec* batch = nullptr) {
     if (!out) return NMPM_ERR_INVALID;
     *out = nullptr;
     if ((dim != 2 && dim != 3) || model < 0 || model > 2 || res < 4 || n > 0xFFFFFFF0ull) {
@@ -288,6 +316,17 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
         return NMPM_ERR_INVALID;
     }
     h->dim = dim, h->model = model, h->res = res, h->n = n;
+    if (batch) {
+        size_t total = 0;
+        for (int k = 0; k < batch->nscenes; ++k) total += batch->counts[k];
+        if (dim != 2 || batch->nscenes < 1 || batch->nscenes > 65535 || total != n || h->opt.slab_x1 > 0 ||
+            h->opt.sort_every < 1 || h->opt.p2g_variant == 1) {
+            g_create_error = "batch: 2D scenes only (1..65535 of them), counts must add up to n, not a slab, with binning";
+            delete h;
+            return NMPM_ERR_INVALID;
+        }
+        h->scenes = batch->nscenes;
+    }
     if (const char* lr = std::getenv("NMPM_LOCAL_REORDER")) h->local_reorder = (*lr != '0');
     h->n_store = n;
     h->slab = h->opt.slab_x1 > 0;
@@ -306,7 +345,7 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
     h->device = h->opt.device;
     fill_params(h, dt, E, nu, gravity);
     const size_t n1 = (size_t) res + 1;
-    h->cells = (dim == 3) ? n1 * n1 * n1 : n1 * n1;
+    h->cells = (dim == 3) ? n1 * n1 * n1 : n1 * n1 * (size_t) h->scenes;  // batch: the scenes' grids stacked along x
     if (h->cells >= 0x7FFFFFFFull) {  // node indices travel as 32-bit signed ints in the P2G packets
         g_create_error = "grid too large: (res+1)^dim must be below 2^31";
         delete h;
@@ -316,6 +355,8 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
     {
         size_t tiles = 1;
         for (int d = 0; d < dim; ++d) tiles *= (size_t) h->tiles_per_axis;
+        if (h->scenes > 1)  // node rows along x: scenes * n1
+            tiles = ((n1 * (size_t) h->scenes + (1 << kTileBits) - 1) >> kTileBits) * (size_t) h->tiles_per_axis;
         int bits = 0;
         while ((1ull << bits) < tiles) ++bits;
         h->key_bits = bits + dim * kTileBits;
@@ -353,14 +394,19 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
         }
     }
     if (dim == 3 && !h->slab) {
-        const char* tl = std::getenv("NMPM_TILES");
-        if (!tl || *tl != '0') {
+        h->tile_policy = h->opt.tiles;
+        if (const char* tl = std::getenv("NMPM_TILES")) h->tile_policy = (*tl == '0') ? 1 : (*tl == '2') ? 2 : 0;
+        if (h->tile_policy != 1) {
             const size_t T = (n1 + 3) / 4, bytes = ((T * T * T + 31) / 32 + 16) * sizeof(uint32_t);
             for (int k = 0; k < kBoxRing; ++k) {
                 CUDA_TRY(h, cudaMalloc(&h->tile_ring[k], bytes));
                 CUDA_TRY(h, cudaMemset(h->tile_ring[k], 0, bytes));
             }
             h->tiles = true;
+            h->tile_want = h->tile_policy == 2;
+            CUDA_TRY(h, cudaMallocHost(&h->h_boxinfo, sizeof(GridBox)));
+            std::memset(h->h_boxinfo, 0, sizeof(GridBox));
+            CUDA_TRY(h, cudaEventCreateWithFlags(&h->boxinfo_ev, cudaEventDisableTiming));
         }
     }
     CUDA_TRY(h, cudaMalloc(&h->d_box, kBoxRing * sizeof(GridBox)));
@@ -388,6 +434,25 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
         CUDA_TRY(h, cudaMalloc(&h->d_ctr, 4 * sizeof(int)));
         const int ctr0[4] = {(int) n, 0, 0, 0};
         CUDA_TRY(h, cudaMemcpy(h->d_ctr, ctr0, sizeof(ctr0), cudaMemcpyHostToDevice));
+    }
+    if (batch && h->scenes >= 1) {
+        std::vector<unsigned short> scene_of(n ? n : 1);
+        h->lame_host.resize((size_t) h->scenes);
+        size_t i = 0;
+        for (int k = 0; k < h->scenes; ++k) {
+            for (size_t c = 0; c < batch->counts[k]; ++c) scene_of[i++] = (unsigned short) k;
+            lame_of(batch->E[k], batch->nu[k], &h->lame_host[k].x, &h->lame_host[k].y);
+        }
+        CUDA_TRY(h, cudaMalloc(&h->d_scene_of, scene_of.size() * sizeof(unsigned short)));
+        CUDA_TRY(h, cudaMemcpy(h->d_scene_of, scene_of.data(), scene_of.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMalloc(&h->d_lame, (size_t) h->scenes * sizeof(float2)));
+        CUDA_TRY(h, cudaMemcpy(h->d_lame, h->lame_host.data(), (size_t) h->scenes * sizeof(float2), cudaMemcpyHostToDevice));
+        h->P.mu_0 = h->lame_host[0].x, h->P.lambda_0 = h->lame_host[0].y;
+        if (h->scenes > 1) {
+            h->P.scenes = h->scenes;
+            h->P.scene_of = h->d_scene_of;
+            h->P.lame = h->d_lame;
+        }
     }
     for (auto& e : h->ev) CUDA_TRY(h, cudaEventCreate(&e));
     return NMPM_OK;
@@ -422,8 +487,12 @@ void nmpm_destroy(nmpm_handle h) {
     free_store(h->store[1]);
     if (h->grid) cudaFree(h->grid);
     if (h->grid_alt) cudaFree(h->grid_alt);
+    if (h->d_scene_of) cudaFree(h->d_scene_of);
+    if (h->d_lame) cudaFree(h->d_lame);
     for (auto* t : h->tile_ring)
         if (t) cudaFree(t);
+    if (h->h_boxinfo) cudaFreeHost(h->h_boxinfo);
+    if (h->boxinfo_ev) cudaEventDestroy(h->boxinfo_ev);
     if (h->d_box) cudaFree(h->d_box);
     if (h->d_box_partial) cudaFree(h->d_box_partial);
     if (h->d_error) cudaFree(h->d_error);
@@ -456,11 +525,11 @@ void nmpm_destroy(nmpm_handle h) {
     delete h;
 }
 
-int nmpm_create(int dim, int model, int res, float dt, float E, float nu, float gravity, size_t n, const float* x,
-                const float* v, const float* F, const float* C, const float* Jp, const float* mass,
-                const float* volume, const nmpm_options* opt, nmpm_handle* out) {
+static int create_soa(int dim, int model, int res, float dt, float E, float nu, float gravity, size_t n, const float* x,
+                      const float* v, const float* F, const float* C, const float* Jp, const float* mass,
+                      const float* volume, const nmpm_options* opt, nmpm_handle* out, const BatchSpec* batch) {
     nmpm_sim* h = nullptr;
-    int rc = create_common(dim, model, res, dt, E, nu, gravity, n, opt, &h);
+    int rc = create_common(dim, model, res, dt, E, nu, gravity, n, opt, &h, batch);
     if (rc != NMPM_OK) {
         if (h) {
             g_create_error = h->last_error;
@@ -518,8 +587,63 @@ int nmpm_create(int dim, int model, int res, float dt, float E, float nu, float 
     return NMPM_OK;
 }
 
+int nmpm_create(int dim, int model, int res, float dt, float E, float nu, float gravity, size_t n, const float* x,
+                const float* v, const float* F, const float* C, const float* Jp, const float* mass,
+                const float* volume, const nmpm_options* opt, nmpm_handle* out) {
+    return create_soa(dim, model, res, dt, E, nu, gravity, n, x, v, F, C, Jp, mass, volume, opt, out, nullptr);
+}
+
+static bool batch_args_ok(int nscenes, const size_t* counts, const float* E, const float* nu, nmpm_handle* out) {
+    if (nscenes >= 1 && counts && E && nu) return true;
+    g_create_error = "batch: nscenes >= 1 and counts, E, nu must not be NULL";
+    if (out) *out = nullptr;
+    return false;
+}
+
+int nmpm_create_batch(int model, int res, float dt, float gravity, int nscenes, const size_t* counts, const float* E,
+                      const float* nu, const float* x, const float* v, const float* F, const float* C, const float* Jp,
+                      const float* mass, const float* volume, const nmpm_options* opt, nmpm_handle* out) {
+    if (!batch_args_ok(nscenes, counts, E, nu, out)) return NMPM_ERR_INVALID;
+    size_t n = 0;
+    for (int k = 0; k < nscenes; ++k) n += counts[k];
+    const BatchSpec b{nscenes, counts, E, nu};
+    return create_soa(2, model, res, dt, E[0], nu[0], gravity, n, x, v, F, C, Jp, mass, volume, opt, out, &b);
+}
+
+static int create_aos(int dim, int model, int res, float dt, float E, float nu, float gravity, size_t n,
+                      const void* particles_aos, size_t stride, const nmpm_options* opt, nmpm_handle* out,
+                      const BatchSpec* batch);
+
 int nmpm_create_aos(int dim, int model, int res, float dt, float E, float nu, float gravity, size_t n,
                     const void* particles_aos, size_t stride, const nmpm_options* opt, nmpm_handle* out) {
+    return create_aos(dim, model, res, dt, E, nu, gravity, n, particles_aos, stride, opt, out, nullptr);
+}
+
+int nmpm_create_batch_aos(int model, int res, float dt, float gravity, int nscenes, const size_t* counts, const float* E,
+                          const float* nu, const void* particles_aos, size_t stride, const nmpm_options* opt,
+                          nmpm_handle* out) {
+    if (!batch_args_ok(nscenes, counts, E, nu, out)) return NMPM_ERR_INVALID;
+    size_t n = 0;
+    for (int k = 0; k < nscenes; ++k) n += counts[k];
+    const BatchSpec b{nscenes, counts, E, nu};
+    return create_aos(2, model, res, dt, E[0], nu[0], gravity, n, particles_aos, stride, opt, out, &b);
+}
+
+int nmpm_num_scenes(nmpm_handle h) { return h ? h->scenes : 0; }
+
+int nmpm_batch_lame(nmpm_handle h, float* mu_0, float* lambda_0) {
+    if (!h) return NMPM_ERR_INVALID;
+    for (int k = 0; k < h->scenes; ++k) {
+        const float2 l = h->lame_host.empty() ? make_float2(h->P.mu_0, h->P.lambda_0) : h->lame_host[(size_t) k];
+        if (mu_0) mu_0[k] = l.x;
+        if (lambda_0) lambda_0[k] = l.y;
+    }
+    return NMPM_OK;
+}
+
+static int create_aos(int dim, int model, int res, float dt, float E, float nu, float gravity, size_t n,
+                      const void* particles_aos, size_t stride, const nmpm_options* opt, nmpm_handle* out,
+                      const BatchSpec* batch) {
     const size_t rec = (dim == 3) ? 112 : 64;
     if ((dim == 2 || dim == 3) && (stride < rec || stride % 4 != 0 || (n && !particles_aos))) {
         g_create_error = "AoS stride must be >= sizeof(Particle<dim>) (64 B in 2D, 112 B in 3D) and a multiple of 4";
@@ -527,7 +651,7 @@ int nmpm_create_aos(int dim, int model, int res, float dt, float E, float nu, fl
         return NMPM_ERR_INVALID;
     }
     nmpm_sim* h = nullptr;
-    int rc = create_common(dim, model, res, dt, E, nu, gravity, n, opt, &h);
+    int rc = create_common(dim, model, res, dt, E, nu, gravity, n, opt, &h, batch);
     if (rc == NMPM_OK && n) {
         rc = ensure_staging(h, n * stride);
         if (rc == NMPM_OK) {
@@ -569,6 +693,7 @@ size_t nmpm_num_slots(nmpm_handle h) { return h ? h->n_store : 0; }
 int nmpm_key_tile_bits(nmpm_handle) { return kTileBits; }
 long long nmpm_launch_count(nmpm_handle h) { return h ? h->launches : 0; }
 int nmpm_fused(nmpm_handle h) { return h ? h->fuse : 0; }
+int nmpm_tiles_active(nmpm_handle h) { return (h && h->tile_want) ? 1 : 0; }
 
 int nmpm_lame(nmpm_handle h, float* mu_0, float* lambda_0) {
     if (!h) return NMPM_ERR_INVALID;
@@ -593,6 +718,17 @@ void* nmpm_get_stream(nmpm_handle h) { return h ? (void*) h->stream : nullptr; }
 // ---------------------------------------------------------------------------------------------
 // the step
 // ---------------------------------------------------------------------------------------------
+// Active node tiles of the positions whose cell keys are `keys` (flags of ring slot `box`); see k_mark_tiles.
+// (Flags left in the slot by a replaced state are only a superset.)
+static void mark_tiles(nmpm_sim* h, const uint32_t* keys, uint32_t n, int box) {
+    h->tile_valid[box] = h->tile_want;
+    if (!h->tile_want || n == 0) return;
+    const unsigned per_block = kMarkWarps * kMarkKeysPerWarp;
+    k_mark_tiles<<<(n + per_block - 1) / per_block, kMarkWarps * 32, 0, h->stream>>>(keys, n, h->tile_ring[box],
+                                                                                    (h->P.n1 + 3) >> 2);
+    h->launches++;
+}
+
 // K0: (keys from the previous G2P, or a key pass) + radix sort.  The reorder itself is fused into the
 // readers: P2G and G2P index the store through h->perm, and G2P writes the other store in sorted order.
 static int do_sort(nmpm_sim* h) {
@@ -605,7 +741,8 @@ static int do_sort(nmpm_sim* h) {
         k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + h->box_cur);
         NMPM_DISPATCH_DIM(h, (k_cell_keys<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(
                                  S, n, h->P, h->tiles_per_axis, h->sort.keys_a, nullptr, h->d_error,
-                                 h->d_box + h->box_cur, h->tiles ? h->tile_ring[h->box_cur] : nullptr)));
+                                 h->d_box + h->box_cur)));
+        mark_tiles(h, h->sort.keys_a, n, h->box_cur);
         h->launches += 2;
         h->box_valid = true;
     }
@@ -638,7 +775,8 @@ static int ensure_box(nmpm_sim* h) {
     k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + h->box_cur);
     NMPM_DISPATCH_DIM(h, (k_cell_keys<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(
                              h->store[h->cur], n, h->P, h->tiles_per_axis, h->sort.keys_b, nullptr, h->d_error,
-                             h->d_box + h->box_cur, h->tiles ? h->tile_ring[h->box_cur] : nullptr)));
+                             h->d_box + h->box_cur)));
+    mark_tiles(h, h->sort.keys_b, n, h->box_cur);
     h->launches += 2;
     h->box_valid = true;
     return NMPM_OK;
@@ -647,10 +785,12 @@ static int ensure_box(nmpm_sim* h) {
 // zero what the P2G of the positions of box `box` scattered into `grid`: their flagged tiles (lowering the flags), or the
 // node box itself
 static void clear_grid(nmpm_sim* h, float4* grid, int box) {
-    if (h->tiles) {
+    if (h->tile_valid[box]) {
         k_tiles3<0><<<kBoxBlocks, 256, 0, h->stream>>>(grid, h->tile_ring[box], h->P);
+        h->tile_valid[box] = false;  // lowered
     } else {
-        NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(grid, h->d_box + box, h->P.n1)));
+        NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(grid, h->d_box + box, h->P.n1,
+                                                                                h->scenes > 1 ? h->scenes * h->P.n1 : 0)));
     }
     h->launches++;
 }
@@ -718,7 +858,7 @@ static int do_p2g(nmpm_sim* h) {
 }
 
 static int do_grid_op(nmpm_sim* h) {
-    if (h->tiles) {
+    if (h->tile_valid[h->box_cur]) {
         k_tiles3<1><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->tile_ring[h->box_cur], h->P);
     } else {
         NMPM_DISPATCH_DIM(h, (k_grid_op<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + h->box_cur, h->P)));
@@ -731,6 +871,7 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
     if (h->n == 0) {
         h->n_store = 0;
         h->box_cur = (h->box_cur + 1) % kBoxRing;
+        h->tile_valid[h->box_cur] = false;
         k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + h->box_cur);
         // an empty slab: its key array is all "gone" marks, and stays aligned with the slots as particles arrive —
         // no key pass may ever run over the (uninitialised) store
@@ -743,54 +884,54 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
     // emit the next step's keys only if the next step sorts
     const bool next_sorts = h->opt.sort_every > 0 && ((h->steps_done + 1) % h->opt.sort_every) == 0;
     // a slab keeps the key array aligned with the slots at all times: it carries the "migrated away" marks
-    uint32_t* keys_out = (next_sorts || h->slab) ? h->sort.keys_a : nullptr;
+    // (and in tile mode: the active node tiles of the coming step are raised from them, mark_tiles below)
+    uint32_t* keys_out = (next_sorts || h->slab || h->tile_want) ? h->sort.keys_a : nullptr;
     const uint32_t* gone_keys = (h->dev_counts || (h->slab && !h->perm && h->n_gone)) ? h->sort.keys_a : nullptr;
     const int box_next = (h->box_cur + 1) % kBoxRing;
-    uint32_t* tiles_next = h->tiles ? h->tile_ring[box_next] : nullptr;  // active node tiles of the coming step
     k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + box_next);
     // fused G2P+P2G: not on the first step after an upload (fuse == 1) — that state is likely to be replaced again
     const bool fused = h->fuse && !mig.left && (h->fuse == 2 || h->steps_done > 0);
     if (fused) {
         if (h->model == 0)
             launch_g2p_p2g<0>(S, T, h->perm, n, h->P, h->grid, h->grid_alt, keys_out, h->tiles_per_axis, h->d_error,
-                              h->d_box_partial, h->local_reorder ? 1 : 0, tiles_next, h->stream, h->fused_minb);
+                              h->d_box_partial, h->local_reorder ? 1 : 0, h->stream, h->fused_minb);
         else if (h->model == 1)
             launch_g2p_p2g<1>(S, T, h->perm, n, h->P, h->grid, h->grid_alt, keys_out, h->tiles_per_axis, h->d_error,
-                              h->d_box_partial, h->local_reorder ? 1 : 0, tiles_next, h->stream, h->fused_minb);
+                              h->d_box_partial, h->local_reorder ? 1 : 0, h->stream, h->fused_minb);
         else
             launch_g2p_p2g<2>(S, T, h->perm, n, h->P, h->grid, h->grid_alt, keys_out, h->tiles_per_axis, h->d_error,
-                              h->d_box_partial, h->local_reorder ? 1 : 0, tiles_next, h->stream, h->fused_minb);
+                              h->d_box_partial, h->local_reorder ? 1 : 0, h->stream, h->fused_minb);
         h->p2g_ahead = true;
     } else if (h->g2p_window && h->g2p_pipe) {  // 3D only: persistent CTAs, pipelined rows (cp.async) and node windows (TMA)
         const unsigned chunks = blocks_for(n, 128);
         const unsigned grid_ctas = chunks < (unsigned) (148 * NMPM_G2P_PIPE_MINB) ? chunks : (unsigned) (148 * NMPM_G2P_PIPE_MINB);
         if (h->model == 0)
             k_g2p_pipe<0><<<grid_ctas, 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error,
-                                                            mig, h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map, tiles_next);
+                                                            mig, h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
         else if (h->model == 1)
             k_g2p_pipe<1><<<grid_ctas, 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error,
-                                                            mig, h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map, tiles_next);
+                                                            mig, h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
         else
             k_g2p_pipe<2><<<grid_ctas, 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error,
-                                                            mig, h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map, tiles_next);
+                                                            mig, h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
     } else if (h->g2p_window) {  // 3D only (set at creation): one-shot CTAs with a TMA-staged node window
         constexpr int D = 3;
         if (h->model == 0)
             k_g2p_gather<D, 0, true><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out,
                                                                                h->tiles_per_axis, h->d_error, mig, h->d_box_partial,
-                                                                               gone_keys, h->local_reorder ? 1 : 0, h->grid_map, tiles_next);
+                                                                               gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
         else if (h->model == 1)
             k_g2p_gather<D, 1, true><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out,
                                                                                h->tiles_per_axis, h->d_error, mig, h->d_box_partial,
-                                                                               gone_keys, h->local_reorder ? 1 : 0, h->grid_map, tiles_next);
+                                                                               gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
         else
             k_g2p_gather<D, 2, true><<<blocks_for(n, 128), 128, 0, h->stream>>>(S, T, h->perm, n, h->P, h->grid, keys_out,
                                                                                h->tiles_per_axis, h->d_error, mig, h->d_box_partial,
-                                                                               gone_keys, h->local_reorder ? 1 : 0, h->grid_map, tiles_next);
+                                                                               gone_keys, h->local_reorder ? 1 : 0, h->grid_map);
     } else {
         NMPM_DISPATCH(h, (k_g2p_gather<D, MODEL, false><<<blocks_for(n, 128), 128, 0, h->stream>>>(
                              S, T, h->perm, n, h->P, h->grid, keys_out, h->tiles_per_axis, h->d_error, mig,
-                             h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map, tiles_next)));
+                             h->d_box_partial, gone_keys, h->local_reorder ? 1 : 0, h->grid_map)));
     }
     {   // warps of the launch above (128-thread CTAs): every one of them wrote a partial box
         const uint32_t nwarps = blocks_for(n, 128) * 4u - ((blocks_for(n, 128) * 128u - n) / 32u);
@@ -798,10 +939,11 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
         k_box_reduce<<<rb, 256, 0, h->stream>>>(h->d_box_partial, nwarps, h->d_box + box_next);
     }
     h->launches += 3;
+    mark_tiles(h, h->sort.keys_a, n, box_next);
     h->box_cur = box_next;
     if (h->perm) h->cur ^= 1;
     h->perm = nullptr;
-    h->keys_valid = next_sorts || h->slab;
+    h->keys_valid = keys_out != nullptr;
     h->n_store = h->n;  // a sorted write compacted the store; an in-place step keeps its slots (incl. gone ones)
     return NMPM_OK;
 }
@@ -890,7 +1032,10 @@ static int graph_steps(nmpm_sim* h, int count) {
     const int gsel0 = h->grid_sel;
     const int key = h->cur | (h->keys_valid ? 2 : 0) | (box0 << 2) | (boxv0 ? 16 : 0) |
                     ((se > 0 ? (int) (h->steps_done % se) : 0) << 5) | (count << 12) | (ahead0 ? 1 << 20 : 0) | (gsel0 << 21) |
-                    ((h->fuse == 1 && h->steps_done == 0) ? 1 << 22 : 0);
+                    ((h->fuse == 1 && h->steps_done == 0) ? 1 << 22 : 0) | (h->tile_want ? 1 << 23 : 0) |
+                    (h->tile_valid[0] ? 1 << 24 : 0) | (h->tile_valid[1] ? 1 << 25 : 0) | (h->tile_valid[2] ? 1 << 26 : 0) |
+                    (h->tile_valid[3] ? 1 << 27 : 0);
+    const bool tv0[kBoxRing] = {h->tile_valid[0], h->tile_valid[1], h->tile_valid[2], h->tile_valid[3]};
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
         if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
@@ -921,12 +1066,14 @@ static int graph_steps(nmpm_sim* h, int count) {
             h->perm = nullptr;
             if (h->grid_sel != gsel0) std::swap(h->grid, h->grid_alt), h->grid_sel = gsel0;
             h->p2g_ahead = ahead0;
+            for (int k = 0; k < kBoxRing; ++k) h->tile_valid[k] = tv0[k];
             return graph_steps(h, count);
         }
         sg.cur_after = h->cur;
         sg.keys_valid_after = h->keys_valid;
         sg.box_after = h->box_cur;
         sg.ahead_after = h->p2g_ahead;
+        for (int k = 0; k < kBoxRing; ++k) sg.tile_valid_after[k] = h->tile_valid[k];
         sg.grid_sel_after = h->grid_sel;
         sg.launches = (int) (h->launches - l0);
         it = h->graphs.emplace(key, sg).first;
@@ -941,10 +1088,42 @@ static int graph_steps(nmpm_sim* h, int count) {
     h->perm = nullptr;
     h->grid_valid = true;
     h->p2g_ahead = it->second.ahead_after;
+    for (int k = 0; k < kBoxRing; ++k) h->tile_valid[k] = it->second.tile_valid_after[k];
     if (h->grid_sel != it->second.grid_sel_after) std::swap(h->grid, h->grid_alt), h->grid_sel = it->second.grid_sel_after;
     h->steps_done += count;
     h->launches += it->second.launches;
     return NMPM_OK;
+}
+
+// Adaptive tile mode: the node box of a recent step travels to pinned memory behind the steps (no host wait); the next
+// call looks at it if it has landed.  Tiles pay when the box is mostly empty: wanted above 1.5 nodes per particle (a
+// compact 8-per-cell block has ~0.4), dropped again below 1.0.
+static void post_boxinfo(nmpm_sim* h) {
+    if (!h->tiles || h->tile_policy != 0 || h->boxinfo_pending || !h->box_valid) return;
+    if (cudaMemcpyAsync(h->h_boxinfo, h->d_box + h->box_cur, sizeof(GridBox), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+        cudaEventRecord(h->boxinfo_ev, h->stream) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    h->boxinfo_pending = true;
+}
+static void update_tile_want(nmpm_sim* h) {
+    if (!h->tiles || h->tile_policy != 0 || !h->boxinfo_pending) return;
+    if (cudaEventQuery(h->boxinfo_ev) != cudaSuccess) {
+        cudaGetLastError();
+        return;  // still in flight: decide later
+    }
+    h->boxinfo_pending = false;
+    const GridBox* b = reinterpret_cast<const GridBox*>(h->h_boxinfo);
+    double vol = 1.0;
+    for (int d = 0; d < 3; ++d) {
+        const int lo = b->lo[d] < 0 ? 0 : b->lo[d], hi = (b->hi[d] + 2 > h->P.n1 - 1) ? h->P.n1 - 1 : b->hi[d] + 2;
+        vol *= hi >= lo ? (double) (hi - lo + 1) : 0.0;
+    }
+    const double per_particle = h->n ? vol / (double) h->n : 0.0;
+    if (!h->tile_want && per_particle > 1.5) h->tile_want = true;
+    else if (h->tile_want && per_particle < 1.0)
+        h->tile_want = false;
 }
 
 // host states repeat with this period (sort cadence x store parity, node-box ring)
@@ -970,10 +1149,12 @@ int nmpm_advance(nmpm_handle h, int nsteps) {
     if (int rc = poll_error(h)) return rc;
     const int cyc = graph_cycle(h);
     for (int s = 0; s < nsteps;) {
+        update_tile_want(h);
         // whole cycles in one graph once the state is periodic (keys and box valid: i.e. not the very first step)
         const int k = (nsteps - s >= cyc && cyc <= 64 && h->steps_done >= cyc && h->steps_done % cyc == 0) ? cyc : 1;
         if (int rc = graph_steps(h, k)) return rc;
         s += k;
+        post_boxinfo(h);
     }
     CUDA_TRY(h, cudaMemcpyAsync(h->h_error, h->d_error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     return NMPM_OK;

@@ -32,8 +32,7 @@ __global__ void __launch_bounds__(128, MINB) k_g2p_p2g(ParticleStore S, Particle
                                                                  uint32_t n, MaterialParams P, const float4* __restrict__ grid,
                                                                  float4* __restrict__ grid_next, uint32_t* __restrict__ keys_out,
                                                                  int tiles_per_axis, int* __restrict__ error_flag,
-                                                                 int* __restrict__ box_partial, int local_reorder,
-                                                                 uint32_t* __restrict__ tile_flags_next) {
+                                                                 int* __restrict__ box_partial, int local_reorder) {
     constexpr int D = 3;
     constexpr int CH = 11;  // float4 chunks per particle packet (k_p2g_cols)
     __shared__ float4 pkt[4][32 * CH];
@@ -149,7 +148,6 @@ __global__ void __launch_bounds__(128, MINB) k_g2p_p2g(ParticleStore S, Particle
         }
         if (keys_out) keys_out[dst] = key;
         box_partial_write<D>(box_partial, live, b, true, i >> 5);
-        if (tile_flags_next) tile_mark_warp(tile_flags_next, live, b, node_tiles_per_axis(n1));  // active tiles of step n+1
 
         // ---- packet of step n+1's scatter, at the particle's NEW place in the warp ------------------------------
         float fx[D], w[D][3];
@@ -246,12 +244,11 @@ __global__ void k_promote_error(int* __restrict__ error_flag) {
 template <int MODEL>
 inline void launch_g2p_p2g(const ParticleStore& S, const ParticleStore& T, const uint32_t* perm, uint32_t n, const MaterialParams& P,
                            const float4* grid, float4* grid_next, uint32_t* keys_out, int tiles_per_axis, int* error_flag,
-                           int* box_partial, int local_reorder, uint32_t* tile_flags_next, cudaStream_t st,
-                           int minb = NMPM_FUSED_MINB) {
+                           int* box_partial, int local_reorder, cudaStream_t st, int minb = NMPM_FUSED_MINB) {
     const unsigned blocks = (n + 127) / 128;
 #define NMPM_FUSED_LAUNCH(B)                                                                                                \
     k_g2p_p2g<MODEL, B><<<blocks, 128, 0, st>>>(S, T, perm, n, P, grid, grid_next, keys_out, tiles_per_axis, error_flag, \
-                                                box_partial, local_reorder, tile_flags_next)
+                                                box_partial, local_reorder)
     // CTAs per SM = register budget: 8 -> 64 registers, 6 -> 80, 5 -> 96 (NMPM_FUSED_MINB env: experiments)
     if (minb >= 8) NMPM_FUSED_LAUNCH(8);
     else if (minb == 7) NMPM_FUSED_LAUNCH(7);

@@ -209,48 +209,81 @@ __global__ void __launch_bounds__(256) k_clear_box(float4* __restrict__ grid, co
 // grid_op and the clear visit only flagged tiles (the clear also lowers the flags).  The flag array of the whole 513^3
 // grid is 268 KB, so it is simply scanned in full: no compaction, no box.
 // A stencil with base b covers nodes b..b+2 per axis, i.e. the tile of b and, where (b & 3) >= 2, the next one.
-struct TileMark {
-    uint32_t lo;   // tile of the base node (linear, x slowest)
-    int straddle;  // bit 0/1/2: the stencil reaches into the next tile along x/y/z
-};
 __device__ __forceinline__ int node_tiles_per_axis(int n1) { return (n1 + 3) >> 2; }
-__device__ __forceinline__ TileMark tile_mark3(const int (&b)[3], int T) {
-    TileMark m;
-    m.lo = (uint32_t) (((b[0] >> 2) * T + (b[1] >> 2)) * T + (b[2] >> 2));
-    m.straddle = ((b[0] & 3) >= 2 ? 1 : 0) | ((b[1] & 3) >= 2 ? 2 : 0) | ((b[2] & 3) >= 2 ? 4 : 0);
-    return m;
-}
-// Raised by whoever produces the next step's positions (G2P, the key pass) — like the node box, and at the same places —
-// once per WARP and distinct tile, not per particle or per run: the lanes of a warp whose stencils start in the same tile
-// (__match_any_sync; 32 cell-sorted particles sit in 1-3 tiles) OR their corner sets together and their first lane does
-// the work.  The flags are BITS (32 tiles per word) raised with a 32-bit reduction (RED.OR at the L2) after a test through
-// L1: a flag only goes 0 -> 1 while the kernel runs, so a stale 0 costs one redundant reduction and nothing else.
-// Measured on cfg4 (gpurun r2u-r2y): one flag BYTE per tile raised with plain stores costs +0.4 ms per step — 4 M one-byte
-// partial-sector writes; every other store of the step fills whole 32-byte sectors — and raising them from the P2G
-// kernels' run flushes instead +0.3 ms.  All loads are issued before the first reduction.  Called by the lanes of `live`.
-__device__ __forceinline__ void tile_mark_warp(uint32_t* flags, unsigned live, const int (&b)[3], int T) {
-    const TileMark m = tile_mark3(b, T);
-    unsigned cm = 1u;  // bit c: corner tile c = (c&1 ? +x) (c&2 ? +y) (c&4 ? +z) is covered by this lane's stencil
-    if (m.straddle & 1) cm |= cm << 1;
-    if (m.straddle & 2) cm |= cm << 2;
-    if (m.straddle & 4) cm |= cm << 4;
-    const unsigned peers = __match_any_sync(live, m.lo);
-    const unsigned um = __reduce_or_sync(peers, cm);
-    if ((int) (threadIdx.x & 31) != __ffs(peers) - 1) return;
-    unsigned set = 0u;
+
+// Raised from the cell KEYS of the coming step (G2P and the key pass write one per particle: key = tile << 6 | cell in
+// tile, and the tile of a stencil's base node IS the cell tile), by a kernel of its own right after them.  Raising a
+// flag is a test-then-set on a word that every warp of the same tile wants to touch — measured on cfg4 (gpurun
+// r2u-r3c), extra time per step when it is done inside the particle kernels:
+//   one flag BYTE per tile, plain stores from the P2G run flushes ............ P2G +0.34 ms  (partial-sector writes)
+//   ... test through L1 before the store ...................................... P2G +0.27 ms
+//   bytes, in G2P per warp and tile (match + OR of the corner sets) ........... G2P +0.54 ms  (4 M one-byte stores)
+//   bits, test through L1 + RED.OR, per warp and tile (match) ................. G2P +0.11 ms, fused kernel +0.37 ms
+//   bits, RED.OR without a test, lanes de-duplicated against their left neighbour only .. G2P +3.1 ms
+//   bits, test at the L2 (ld.global.cg) + RED.OR, per warp and tile ........... fused +1.3 ms
+// so here the global traffic is cut at the source: a warp walks 1 024 consecutive (cell-sorted) keys and collects
+// {tile, corners} in a private 32-entry table in shared memory; what it holds at the end goes to memory once (test through
+// L1, then a 32-bit RED.OR).  (x & 3) >= 2 is bit 1 of the 2-bit cell coordinate: key bits 5, 3, 1.
+// The kernel streams 4 B per particle.
+constexpr int kMarkWarps = 8, kMarkKeysPerWarp = 1024;
+__device__ __forceinline__ void tile_raise(uint32_t* __restrict__ flags, uint32_t lo, unsigned corners, int T) {
+    unsigned up = 0u;  // all tests first (through L1: a stale 0 only costs a redundant reduction), then the reductions
 #pragma unroll
     for (int c = 0; c < 8; ++c)
-        if ((um >> c) & 1u) {
-            const uint32_t t = m.lo + (uint32_t) (((c & 1) ? T * T : 0) + ((c & 2) ? T : 0) + ((c & 4) ? 1 : 0));
-            set |= ((__ldca(flags + (t >> 5)) >> (t & 31u)) & 1u) << c;
+        if ((corners >> c) & 1u) {
+            const uint32_t t = lo + (uint32_t) (((c & 1) ? T * T : 0) + ((c & 2) ? T : 0) + ((c & 4) ? 1 : 0));
+            up |= ((__ldca(flags + (t >> 5)) >> (t & 31u)) & 1u) << c;
         }
-    const unsigned todo = um & ~set;
+    corners &= ~up;
 #pragma unroll
     for (int c = 0; c < 8; ++c)
-        if ((todo >> c) & 1u) {
-            const uint32_t t = m.lo + (uint32_t) (((c & 1) ? T * T : 0) + ((c & 2) ? T : 0) + ((c & 4) ? 1 : 0));
+        if ((corners >> c) & 1u) {
+            const uint32_t t = lo + (uint32_t) (((c & 1) ? T * T : 0) + ((c & 2) ? T : 0) + ((c & 4) ? 1 : 0));
             atomicOr(flags + (t >> 5), 1u << (t & 31u));
         }
+}
+__global__ void __launch_bounds__(kMarkWarps * 32) k_mark_tiles(const uint32_t* __restrict__ keys, uint32_t n,
+                                                                uint32_t* __restrict__ flags, int T) {
+    // per warp: 32 entries {tile, corners to raise}; an entry is claimed by the first tile that hashes to it and never
+    // evicted (a tile that finds its entry taken goes to memory directly), the warp flushes its entries once at the end —
+    // so the walk itself waits for no global memory access except the key loads
+    __shared__ unsigned int tag[kMarkWarps][32], mask[kMarkWarps][32];
+    constexpr unsigned kEmpty = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    tag[warp][lane] = kEmpty, mask[warp][lane] = 0u;
+    __syncwarp();
+    const uint32_t first = (blockIdx.x * kMarkWarps + warp) * (uint32_t) kMarkKeysPerWarp;
+    constexpr int B = 8;  // keys per lane in flight
+    for (uint32_t base = first; base < first + kMarkKeysPerWarp && base < n; base += 32u * B) {
+        uint32_t kk[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const uint32_t i = base + (uint32_t) (j * 32 + lane);
+            kk[j] = (i < n) ? __ldg(keys + i) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const uint32_t key = kk[j];
+            const bool valid = key < 0xFFFFFFFEu;  // not "out of grid" / "migrated away"
+            const uint32_t lo = key >> 6;
+            // a lane whose left neighbour starts in the same tile with the same corner set has nothing to add
+            const uint32_t pkey = __shfl_up_sync(0xffffffffu, key, 1);
+            if (valid && (lane == 0 || (pkey >> 6) != lo || ((pkey ^ key) & 0x2Au) != 0u)) {
+                unsigned cm = 1u;  // bit c: corner tile c = (c&1 ? +x) (c&2 ? +y) (c&4 ? +z) is covered by this stencil
+                if (key & 0x20u) cm |= cm << 1;  // (x & 3) >= 2
+                if (key & 0x08u) cm |= cm << 2;  // (y & 3) >= 2
+                if (key & 0x02u) cm |= cm << 4;  // (z & 3) >= 2
+                const unsigned slot = (lo ^ (lo >> 5)) & 31u;
+                const unsigned seen = atomicCAS(&tag[warp][slot], kEmpty, lo);
+                if (seen == kEmpty || seen == lo) atomicOr(&mask[warp][slot], cm);
+                else
+                    tile_raise(flags, lo, cm, T);
+            }
+        }
+    }
+    __syncwarp();
+    const unsigned mine = mask[warp][lane];
+    if (mine) tile_raise(flags, tag[warp][lane], mine, T);
 }
 
 // One warp per flag word (32 consecutive tiles): the warp visits every flagged tile — lane -> (row, half): 16 (x,y) rows
@@ -337,8 +370,7 @@ __device__ __forceinline__ MaterialParams scene_params(const MaterialParams& P, 
 template <int D>
 __global__ void __launch_bounds__(256) k_cell_keys(ParticleStore S, uint32_t n, MaterialParams P, int tiles_per_axis,
                                                    uint32_t* __restrict__ keys, int32_t* __restrict__ base_out,
-                                                   int* __restrict__ error_flag, GridBox* __restrict__ box,
-                                                   uint32_t* tile_flags = nullptr) {
+                                                   int* __restrict__ error_flag, GridBox* __restrict__ box) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float x[D];
@@ -366,9 +398,6 @@ __global__ void __launch_bounds__(256) k_cell_keys(ParticleStore S, uint32_t n, 
         for (int d = 0; d < D; ++d) b[d] = min(max(b[d], 0), P.res - 2);
         b[0] += xoff;
         box_update<D>(box, b, true);
-        if constexpr (D == 3) {
-            if (tile_flags) tile_mark_warp(tile_flags, __activemask(), b, node_tiles_per_axis(P.n1));
-        }
     }
 }
 
@@ -678,8 +707,7 @@ __device__ __forceinline__ void g2p_finish(PState<D>& p, const Mat<D>& Cn, const
                                            const ParticleStore& T, const uint32_t* __restrict__ perm, uint32_t src, uint32_t i,
                                            unsigned live, const MaterialParams& P, uint32_t* __restrict__ keys_out,
                                            int tiles_per_axis, const MigrateArgs& mig, int* __restrict__ box_partial,
-                                           const uint32_t* __restrict__ gone_keys, int local_reorder, int xoff = 0,
-                                           uint32_t* tile_flags_next = nullptr) {
+                                           const uint32_t* __restrict__ gone_keys, int local_reorder, int xoff = 0) {
     g2p_update<D, MODEL>(p, Cn, vn, P);
     // warp-uniform (kernel argument).  Slabs re-group as well: ranks are mapped onto the slots of the warp's LIVE lanes
     // (slots whose particle migrated away keep their "gone" mark and stay where they are).
@@ -763,9 +791,6 @@ __device__ __forceinline__ void g2p_finish(PState<D>& p, const Mat<D>& Cn, const
         b[0] += xoff;
         // migrants stay in the sender's box: the box table of the slab protocol must cover them until they are unpacked
         box_partial_write<D>(box_partial, live, b, true, i >> 5);
-        if constexpr (D == 3) {
-            if (tile_flags_next) tile_mark_warp(tile_flags_next, live, b, node_tiles_per_axis(P.n1));
-        }
     }
 }
 
@@ -787,8 +812,7 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
                                                     uint32_t* __restrict__ keys_out, int tiles_per_axis,
                                                     int* __restrict__ error_flag, MigrateArgs mig,
                                                     int* __restrict__ box_partial, const uint32_t* __restrict__ gone_keys,
-                                                    int local_reorder, const __grid_constant__ CUtensorMap grid_map,
-                                                    uint32_t* tile_flags_next = nullptr) {
+                                                    int local_reorder, const __grid_constant__ CUtensorMap grid_map) {
     static_assert(!WINDOW || D == 3, "the TMA node window is a 3D path");
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // slab mode between sorts: a slot whose particle migrated away is skipped (its key stays kKeyGone)
@@ -920,7 +944,7 @@ __global__ void __launch_bounds__(128, NMPM_G2P_MINB) k_g2p_gather(ParticleStore
         }
     }
     g2p_finish<D, MODEL>(p, Cn, vn, S, T, perm, src, i, live, P, keys_out, tiles_per_axis, mig, box_partial, gone_keys,
-                         local_reorder, xoff, tile_flags_next);
+                         local_reorder, xoff);
 }
 
 // ---- K4, software-pipelined (3D): persistent CTAs, asynchronous particle rows and node windows ------------------------
@@ -945,8 +969,7 @@ __global__ void __launch_bounds__(128, NMPM_G2P_PIPE_MINB) k_g2p_pipe(ParticleSt
                                                                  uint32_t* __restrict__ keys_out, int tiles_per_axis,
                                                                  int* __restrict__ error_flag, MigrateArgs mig,
                                                                  int* __restrict__ box_partial, const uint32_t* __restrict__ gone_keys,
-                                                                 int local_reorder, const __grid_constant__ CUtensorMap grid_map,
-                                                                 uint32_t* tile_flags_next = nullptr) {
+                                                                 int local_reorder, const __grid_constant__ CUtensorMap grid_map) {
     constexpr int D = 3;
     __shared__ __align__(128) float4 win[kWinX * kWinPitch];
     __shared__ __align__(16) float4 rows[4][128];
@@ -1092,7 +1115,7 @@ __global__ void __launch_bounds__(128, NMPM_G2P_PIPE_MINB) k_g2p_pipe(ParticleSt
             }
         } else if (mine) {
             g2p_finish<D, MODEL>(p, Cn, vn, S, T, perm, src, i, live, P, keys_out, tiles_per_axis, mig, box_partial, gone_keys,
-                                 local_reorder, 0, tile_flags_next);
+                                 local_reorder);
         }
     }
 }

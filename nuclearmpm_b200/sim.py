@@ -46,7 +46,7 @@ class MaterialModel(enum.IntEnum):
 class Options(ct.Structure):
     _fields_ = [("device", ct.c_int), ("sort_every", ct.c_int), ("p2g_variant", ct.c_int), ("use_graph", ct.c_int),
                 ("slab_x0", ct.c_int), ("slab_x1", ct.c_int), ("capacity", ct.c_int), ("g2p_window", ct.c_int),
-                ("fuse", ct.c_int), ("reserved", ct.c_int * 7)]
+                ("fuse", ct.c_int), ("tiles", ct.c_int), ("reserved", ct.c_int * 6)]
 
 
 def lib_path() -> Path:
@@ -77,6 +77,11 @@ def load_library():
     sig("nmpm_default_options", None, [ct.POINTER(Options)])
     sig("nmpm_create", ci, [ci, ci, ci, cf, cf, cf, cf, sz] + [_fp] * 7 + [ct.POINTER(Options), ct.POINTER(vp)])
     sig("nmpm_create_aos", ci, [ci, ci, ci, cf, cf, cf, cf, sz, vp, sz, ct.POINTER(Options), ct.POINTER(vp)])
+    szp = ct.POINTER(ct.c_size_t)
+    sig("nmpm_create_batch", ci, [ci, ci, cf, cf, ci, szp, _fp, _fp] + [_fp] * 7 + [ct.POINTER(Options), ct.POINTER(vp)])
+    sig("nmpm_create_batch_aos", ci, [ci, ci, cf, cf, ci, szp, _fp, _fp, vp, sz, ct.POINTER(Options), ct.POINTER(vp)])
+    sig("nmpm_num_scenes", ci, [vp])
+    sig("nmpm_batch_lame", ci, [vp, _fp, _fp])
     sig("nmpm_destroy", None, [vp])
     sig("nmpm_advance", ci, [vp, ci])
     sig("nmpm_phase", ci, [vp, ci])
@@ -102,6 +107,7 @@ def load_library():
     sig("nmpm_timing_read", ci, [vp, _fp, ct.POINTER(ci), ci])
     sig("nmpm_launch_count", ct.c_longlong, [vp])
     sig("nmpm_fused", ci, [vp])
+    sig("nmpm_tiles_active", ci, [vp])
     sig("nmpm_set_stream", ci, [vp, vp])
     sig("nmpm_get_stream", vp, [vp])
     sig("nmpm_grid_plane_ptr", vp, [vp, ci])
@@ -171,7 +177,7 @@ class MPMSimulation:
     def __init__(self, particles, model, res: int = 64, dt: float = 1e-4, E: float = 1e4, nu: float = 0.2,
                  gravity: float = -100.0, *, v=None, F=None, C=None, Jp=None, mass=None, volume=None,
                  device: int = 0, sort_every: int = 4, p2g_variant: int = 0, slab=None, capacity: int = 0,
-                 ids=None, g2p_window: int = 0, fuse: int = 0):
+                 ids=None, g2p_window: int = 0, fuse: int = 0, tiles: int = 0):
         self._L = load_library()
         x = _f32(particles)
         if x.ndim != 2 or x.shape[1] not in (2, 3):
@@ -183,6 +189,7 @@ class MPMSimulation:
         self._L.nmpm_default_options(C_byref(opt))
         opt.device, opt.sort_every, opt.p2g_variant, opt.g2p_window = device, sort_every, p2g_variant, g2p_window
         opt.fuse = int(fuse)   # 0 auto, 1 off, 2 on (not on the first step after an upload), 3 always
+        opt.tiles = int(tiles)  # active node tiles: 0 adaptive, 1 never, 2 always
         if slab is not None:
             opt.slab_x0, opt.slab_x1 = slab
             opt.capacity = int(capacity)
@@ -275,7 +282,7 @@ class MPMSimulation:
 
     def grid(self):
         """grid() (src/nclr.h:87): (velocity (cells,dim), mass (cells,)); empty before the first step."""
-        cells = (self.res + 1) ** self.dim
+        cells = (self.res + 1) ** self.dim * getattr(self, "nscenes", 1)
         gv = np.empty((cells, self.dim), np.float32)
         gm = np.empty((cells,), np.float32)
         got = ct.c_size_t(0)
@@ -343,12 +350,65 @@ class MPMSimulation:
         """1/2 when G2P also scatters the next step's P2G (include/nmpm.h: nmpm_options.fuse), else 0"""
         return int(self._L.nmpm_fused(self._h))
 
+    @property
+    def tiles_active(self) -> bool:
+        """True while grid_op / the grid clear work on active node tiles (nmpm_options.tiles) instead of the node box"""
+        return bool(self._L.nmpm_tiles_active(self._h))
+
     def set_stream(self, cuda_stream: int) -> None:
         self._check(self._L.nmpm_set_stream(self._h, ct.c_void_p(cuda_stream)), "nmpm_set_stream")
 
     @property
     def stream(self) -> int:
         return int(self._L.nmpm_get_stream(self._h) or 0)
+
+
+class MPMBatch(MPMSimulation):
+    """A batch of independent 2D scenes behind one handle (include/nmpm.h: nmpm_create_batch; BASELINE config 5).
+
+    `scenes`: list of (n_s, 2) position arrays; `E`, `nu`: one value per scene.  particles() / upload() / grid() work on
+    the scenes' arrays concatenated; scene_slices gives each scene's range, grids(s) its (res+1)^2 cells."""
+
+    def __init__(self, scenes, model, res: int = 64, dt: float = 1e-4, E=None, nu=None, gravity: float = -100.0, *,
+                 v=None, device: int = 0, sort_every: int = 4):
+        self._L = load_library()
+        xs = [_f32(x) for x in scenes]
+        if not xs or any(x.ndim != 2 or x.shape[1] != 2 for x in xs):
+            raise ValueError("scenes must be a non-empty list of (n, 2) position arrays")
+        self.nscenes = len(xs)
+        counts = np.array([len(x) for x in xs], dtype=np.uintp)
+        x = np.ascontiguousarray(np.concatenate(xs))
+        self.n, self.dim = x.shape
+        self.res, self.model = int(res), MaterialModel(int(model))
+        self.scene_slices = [slice(int(a), int(a + c)) for a, c in zip(np.cumsum(counts) - counts, counts)]
+        Es = _f32(np.full(self.nscenes, 1e4) if E is None else E, (self.nscenes,))
+        nus = _f32(np.full(self.nscenes, 0.2) if nu is None else nu, (self.nscenes,))
+        n, d = self.n, 2
+        opt = Options()
+        self._L.nmpm_default_options(C_byref(opt))
+        opt.device, opt.sort_every = device, sort_every
+        vv = None if v is None else np.ascontiguousarray(np.concatenate([_f32(a) for a in v]))
+        arrs = [x, _f32(vv, (n, d)), _f32(None, (n, d, d)), _f32(None, (n, d, d)), _f32(None, (n,)), _f32(None, (n,)),
+                _f32(None, (n,))]
+        h = C_void_p()
+        rc = self._L.nmpm_create_batch(int(model), int(res), dt, gravity, self.nscenes,
+                                       counts.ctypes.data_as(ct.POINTER(ct.c_size_t)), _p(Es), _p(nus),
+                                       *[_p(a) for a in arrs], C_byref(opt), C_byref(h))
+        if rc != 0:
+            raise NmpmError(f"nmpm_create_batch failed ({rc}): {self._L.nmpm_last_error(None).decode()}")
+        self._h = h
+        mu, lam = np.empty(self.nscenes, np.float32), np.empty(self.nscenes, np.float32)
+        self._L.nmpm_batch_lame(self._h, _p(mu), _p(lam))
+        self.mu_0, self.lambda_0 = mu, lam
+
+    def scene_particles(self, s: int, state: dict | None = None) -> dict:
+        state = state or self.particles()
+        return {k: a[self.scene_slices[s]] for k, a in state.items()}
+
+    def grids(self, s: int, grid=None):
+        gv, gm = grid or self.grid()
+        cells = (self.res + 1) ** 2
+        return gv[s * cells:(s + 1) * cells], gm[s * cells:(s + 1) * cells]
 
 
 def C_byref(x):

@@ -21,6 +21,9 @@ minb6)   NMPM_FUSED_MINB=6 timeout 600 python bench.py --steps 20 --warmup 5 --n
 abtile)  for cfg in "0 1" "0 0" "1 0" "2 0" "3 0"; do set -- $cfg; NMPM_TILE_MODE=$1 NMPM_TILES_CONSUME=$2 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --late-step 0 --fuse 1 > $out/bench_tm$1_c$2.json 2> $out/bench_tm$1_c$2.err; echo "tile mode $1 consume $2 rc=$?"; python tools/bench_summary.py $out/bench_tm$1_c$2.json; done;;
 ncug2p)  NMPM_FUSE=0 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_g2p_gather' -s 30 -c 2 \
             -f -o $out/prof_cfg4_g2p python tools/profile_step.py --workload cfg4 --warmup 28 --steps 6 --sort-every 4 > $out/ncu_g2p.log 2>&1; echo "ncu rc=$?"; tail -2 $out/ncu_g2p.log;;
+batchtest) timeout 600 python -m pytest tests/test_batch_gpu.py -m gpu -q -x > $out/pytest_batch.log 2>&1; echo "batch pytest rc=$?"; tail -25 $out/pytest_batch.log;;
+tiletest) timeout 600 python -m pytest tests/test_tiles_gpu.py -m gpu -q -x > $out/pytest_tiles.log 2>&1; echo "tiles pytest rc=$?"; tail -25 $out/pytest_tiles.log;;
+alwaystiles) NMPM_TILES=2 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu > $out/bench_quick_alwaystiles.json 2> $out/bench_quick_alwaystiles.err; echo "bench always tiles rc=$?"; python tools/bench_summary.py $out/bench_quick_alwaystiles.json;;
 smoke)   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $out/smoke.log;;
 bench)   timeout 900 python bench.py --steps 20 --warmup 5 > $out/bench_default.json 2> $out/bench_default.err; echo "bench rc=$?"; tail -3 $out/bench_default.err; python tools/bench_summary.py $out/bench_default.json;;
 quick)   timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu > $out/bench_quick.json 2> $out/bench_quick.err; echo "bench rc=$?"; tail -3 $out/bench_quick.err; python tools/bench_summary.py $out/bench_quick.json;;
