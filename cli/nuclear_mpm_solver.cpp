@@ -14,8 +14,9 @@
 //
 // Extensions (not in the reference):
 //   --scenes FILE [--out-dir DIR]   dataset generation (BASELINE.json config 5): every non-empty line of FILE
-//                    is the flag list of one scene; all scenes are advanced concurrently on the GPU (one
-//                    simulation and CUDA stream each) and dumped to DIR/scene_<k>/tmp/...
+//                    is the flag list of one scene; scenes that share model / steps / gravity are advanced as ONE
+//                    batched simulation (nclr::MPMBatch2D: one set of kernel launches per step for all of them;
+//                    NMPM_CLI_BATCH=0: one simulation and CUDA stream per scene) and dumped to DIR/scene_<k>/tmp/...
 //   --dump-bin       additionally write tmp/{step}_particles.bin (raw Particle<2> records) per step
 //   --parse-only     print the parsed configuration and exit (used by the CPU tests of the flag rules)
 // dim 3 is accepted like in the reference and, like there, builds an empty simulation and does nothing (Q16).
@@ -33,6 +34,7 @@
 #include <exception>
 #include <chrono>
 #include <thread>
+#include <tuple>
 #include <vector>
 
 #include "nclr.h"
@@ -308,6 +310,108 @@ static void run_scenes(std::vector<Scene> &scenes) {
     std::cout << "Simulation done" << std::endl;
 }
 
+// ---- scene lists as batches: scenes that share model / steps / gravity live in ONE simulation (nclr::MPMBatch2D: the
+// scenes' grids stacked in one tall grid, one set of kernel launches per step for all of them).  64 scenes of 1 250
+// particles are dispatch-bound one by one (~14 kernels of a few microseconds per scene and step).
+struct Group {
+    std::vector<size_t> members;  // indices into `scenes`
+    std::unique_ptr<nclr::MPMBatch2D> sim;
+    int steps = 0;
+};
+
+static std::vector<Group> make_groups(const std::vector<Scene> &scenes) {
+    std::vector<Group> groups;
+    std::vector<std::tuple<int, int, nclr::real>> keys;
+    for (size_t k = 0; k < scenes.size(); ++k) {
+        const auto &c = scenes[k].cfg;
+        const auto key = std::make_tuple(static_cast<int>(c.model), c.steps, c.gravity);
+        size_t g = 0;
+        while (g < keys.size() && keys[g] != key) ++g;
+        if (g == keys.size()) {
+            keys.push_back(key);
+            groups.emplace_back();
+            groups.back().steps = c.steps;
+        }
+        groups[g].members.push_back(k);
+    }
+    for (auto &g : groups) {
+        std::vector<std::vector<nclr::Particle<2>>> parts;
+        std::vector<nclr::real> E, nu;
+        for (const size_t k : g.members) {
+            parts.push_back(generate_cubes(scenes[k].cfg));
+            E.push_back(scenes[k].cfg.E);
+            nu.push_back(scenes[k].cfg.nu);
+        }
+        const auto &c = scenes[g.members[0]].cfg;
+        g.sim = std::make_unique<nclr::MPMBatch2D>(parts, c.model, kGridResolution, kDt, E, nu, c.gravity);
+    }
+    return groups;
+}
+
+static void run_group(const std::vector<Scene> &scenes, Group &g) {
+    bool any_dump = false;
+    for (const size_t k : g.members) any_dump = any_dump || scenes[k].cfg.dump;
+    if (!any_dump) {
+        constexpr int kBlock = 64;  // whole CUDA-graph cycles per call
+        for (int step = 0; step < g.steps; step += kBlock) g.sim->advance(std::min(kBlock, g.steps - step));
+        g.sim->synchronize();
+        return;
+    }
+    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nthreads = std::min({g.members.size(), hw, size_t(16)});
+    const std::vector<nclr::Cell<2>> empty_grid((kGridResolution + 1) * (kGridResolution + 1), nclr::Cell<2>());
+    for (int step = 0; step < g.steps; ++step) {
+        // snapshot BEFORE the step (src/solver.cpp:50-58): one download of the batch, then the text files scene by scene
+        (void) g.sim->particles(0);
+        if (step > 0) (void) g.sim->grid(0);
+        auto write_range = [&](size_t first) {
+            for (size_t m = first; m < g.members.size(); m += nthreads) {
+                const auto &s = scenes[g.members[m]];
+                if (!s.cfg.dump) continue;
+                dump_particles(s.tmp, step, s.cfg, g.sim->mu_0(m), g.sim->lambda_0(m), g.sim->particles(m));
+                dump_cells(s.tmp, step, step > 0 ? g.sim->grid(m) : empty_grid);
+            }
+        };
+        if (nthreads <= 1) {
+            write_range(0);
+        } else {
+            std::vector<std::thread> pool;
+            std::vector<std::exception_ptr> errors(nthreads);
+            for (size_t t = 0; t < nthreads; ++t)
+                pool.emplace_back([&, t] {
+                    try {
+                        write_range(t);
+                    } catch (...) {
+                        errors[t] = std::current_exception();
+                    }
+                });
+            for (auto &th : pool) th.join();
+            for (auto &e : errors)
+                if (e) std::rethrow_exception(e);
+        }
+        g.sim->advance();
+    }
+    g.sim->synchronize();
+}
+
+static void run_groups(const std::vector<Scene> &scenes, std::vector<Group> &groups) {
+    std::cout << "Running simulation" << std::endl;
+    std::vector<std::thread> pool;  // the groups are independent: one host thread each (three for config 5)
+    std::vector<std::exception_ptr> errors(groups.size());
+    for (size_t g = 0; g < groups.size(); ++g)
+        pool.emplace_back([&, g] {
+            try {
+                run_group(scenes, groups[g]);
+            } catch (...) {
+                errors[g] = std::current_exception();
+            }
+        });
+    for (auto &th : pool) th.join();
+    for (auto &e : errors)
+        if (e) std::rethrow_exception(e);
+    std::cout << "Simulation done" << std::endl;
+}
+
 static std::vector<std::string> split_ws(const std::string &line) {
     std::istringstream is(line);
     std::vector<std::string> out;
@@ -389,13 +493,23 @@ int main(int argc, char **argv) {
             return EXIT_SUCCESS;
         }
         const auto t_start = std::chrono::steady_clock::now();
-        for (auto &s : scenes)
-            s.sim = std::make_unique<nclr::MPMSimulation<2>>(generate_cubes(s.cfg), s.cfg.model, kGridResolution, kDt, s.cfg.E,
-                                                             s.cfg.nu, s.cfg.gravity);
+        // a scene list runs as batches (NMPM_CLI_BATCH=0: one simulation per scene, spread over host threads)
+        const char *batch_env = std::getenv("NMPM_CLI_BATCH");
+        const bool batched = scenes_file && !scenes_file->empty() && !(batch_env && *batch_env == '0');
+        std::vector<Group> groups;
+        if (batched) {
+            groups = make_groups(scenes);
+        } else {
+            for (auto &s : scenes)
+                s.sim = std::make_unique<nclr::MPMSimulation<2>>(generate_cubes(s.cfg), s.cfg.model, kGridResolution, kDt,
+                                                                 s.cfg.E, s.cfg.nu, s.cfg.gravity);
+        }
         bool any_dump = false;
         for (const auto &s : scenes) any_dump = any_dump || s.cfg.dump;
         const auto t_setup = std::chrono::steady_clock::now();
-        run_scenes(scenes);
+        if (batched) run_groups(scenes, groups);
+        else
+            run_scenes(scenes);
         if (std::getenv("NMPM_CLI_TIMING")) {  // where the wall time of a batch goes (tools/bench_cfg5.py)
             const auto t_end = std::chrono::steady_clock::now();
             std::cerr << "{\"setup_s\": " << std::chrono::duration<double>(t_setup - t_start).count()

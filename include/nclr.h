@@ -419,4 +419,85 @@ namespace nclr {
         const int res_;
         nmpm_handle handle_ = nullptr;
     };
+
+    // Extension (no counterpart in the reference, which runs one scene per process — src/solver.cpp:45-62): a batch of
+    // independent 2D scenes with the same model / res / dt / gravity behind ONE simulation (nmpm_create_batch_aos), advanced
+    // by the same kernel launches.  Each scene evolves as it would alone (up to the order of floating-point sums).
+    class MPMBatch2D {
+    public:
+        MPMBatch2D(const std::vector<std::vector<Particle<2>>> &scenes, const MaterialModel model, int res, real dt,
+                   const std::vector<real> &E, const std::vector<real> &nu, real gravity)
+            : res_(res) {
+            if (scenes.empty() || E.size() != scenes.size() || nu.size() != scenes.size())
+                throw std::invalid_argument("nclr::MPMBatch2D: one E and one nu per scene");
+            std::vector<size_t> counts;
+            offsets_.push_back(0);
+            for (const auto &sc : scenes) {
+                counts.push_back(sc.size());
+                particles_.insert(particles_.end(), sc.begin(), sc.end());
+                offsets_.push_back(particles_.size());
+            }
+            const int rc = nmpm_create_batch_aos(static_cast<int>(model), res, dt, gravity, static_cast<int>(scenes.size()),
+                                                 counts.data(), E.data(), nu.data(), particles_.data(), sizeof(Particle<2>),
+                                                 nullptr, &handle_);
+            if (rc != NMPM_OK) {
+                const std::string why = nmpm_last_error(nullptr);
+                handle_ = nullptr;
+                throw std::runtime_error("nclr::MPMBatch2D: " + why);
+            }
+            mu_0_.resize(scenes.size()), lambda_0_.resize(scenes.size());
+            nmpm_batch_lame(handle_, mu_0_.data(), lambda_0_.data());
+        }
+        ~MPMBatch2D() { nmpm_destroy(handle_); }
+        MPMBatch2D(const MPMBatch2D &) = delete;
+        MPMBatch2D &operator=(const MPMBatch2D &) = delete;
+
+        auto scenes() const -> size_t { return offsets_.size() - 1; }
+        auto mu_0(size_t s) const -> real { return mu_0_.at(s); }
+        auto lambda_0(size_t s) const -> real { return lambda_0_.at(s); }
+
+        auto advance(int steps = 1) -> void {
+            particles_dirty_ = grid_dirty_ = true;
+            check(nmpm_advance(handle_, steps));
+        }
+        auto synchronize() const -> void { check(nmpm_synchronize(handle_)); }
+
+        // particles of scene s, input order (one download of the whole batch per step, shared by all scenes)
+        auto particles(size_t s) const -> std::vector<Particle<2>> {
+            if (particles_dirty_) {
+                check(nmpm_download_particles_aos(handle_, particles_.data(), sizeof(Particle<2>)));
+                particles_dirty_ = false;
+            }
+            return std::vector<Particle<2>>(particles_.begin() + offsets_.at(s), particles_.begin() + offsets_.at(s + 1));
+        }
+        // grid of scene s: (res+1)^2 cells in the reference's order; empty before the first advance()
+        auto grid(size_t s) const -> std::vector<Cell<2>> {
+            if (grid_dirty_) {
+                cells_.assign(nmpm_grid_cells(handle_), Cell<2>());
+                size_t got = 0;
+                check(nmpm_download_grid_aos(handle_, cells_.data(), sizeof(Cell<2>), &got));
+                cells_.resize(got);
+                grid_dirty_ = false;
+            }
+            if (cells_.empty()) return {};
+            const size_t per = size_t(res_ + 1) * size_t(res_ + 1);
+            return std::vector<Cell<2>>(cells_.begin() + s * per, cells_.begin() + (s + 1) * per);
+        }
+
+    private:
+        auto check(int rc) const -> void {
+            if (rc == NMPM_OK) return;
+            const std::string why = nmpm_last_error(handle_);
+            if (rc == NMPM_ERR_OUT_OF_GRID) throw std::out_of_range("nclr::MPMBatch2D: " + why);
+            throw std::runtime_error("nclr::MPMBatch2D: " + why);
+        }
+        mutable std::vector<Particle<2>> particles_;
+        mutable std::vector<Cell<2>> cells_;
+        std::vector<size_t> offsets_;
+        std::vector<real> mu_0_, lambda_0_;
+        mutable bool particles_dirty_ = false;
+        mutable bool grid_dirty_ = false;
+        const int res_;
+        nmpm_handle handle_ = nullptr;
+    };
 }// namespace nclr

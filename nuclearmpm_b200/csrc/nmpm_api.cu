@@ -75,15 +75,10 @@ struct nmpm_sim {
     std::vector<float2> lame_host;
     uint32_t* tile_ring[kBoxRing] = {nullptr, nullptr, nullptr, nullptr};
     bool tiles = false;      // flag arrays allocated (3D, single GPU)
-    // Tile mode is adaptive: a compact block fills its node box and the flags only cost time (+3 % of G2P), a dispersed
-    // scene (cfg4 after ~100 steps) leaves 85-90 % of the box empty.  `tile_want` follows the box volume read back
-    // without a host wait (h_boxinfo); flags are valid only for ring slots whose positions were produced while it was on.
+    // Tile mode is adaptive and decided on the device per step (k_tile_decide): d_tile_want[b] says whether the flags of ring
+    // slot b were raised for the positions box[b] bounds; every tile / box kernel checks it and returns if it is not its turn.
     int tile_policy = 0;     // nmpm_options.tiles: 0 adaptive, 1 never, 2 always
-    bool tile_want = false;
-    bool tile_valid[kBoxRing] = {false, false, false, false};
-    int* h_boxinfo = nullptr;         // pinned copy of a recent GridBox (8 ints)
-    cudaEvent_t boxinfo_ev = nullptr;
-    bool boxinfo_pending = false;  // CTAs per SM the fused kernel is compiled for (env NMPM_FUSED_MINB: experiments)
+    int* d_tile_want = nullptr;  // kBoxRing ints  // CTAs per SM the fused kernel is compiled for (env NMPM_FUSED_MINB: experiments)
     // node boxes (GridBox, device): box[box_cur] bounds the particles of the current step, box[(box_cur+3)%4]
     // the nodes the previous P2G wrote (cleared at the start of the next one), box[(box_cur+1)%4] is being
     // built by the G2P in flight
@@ -138,7 +133,6 @@ struct nmpm_sim {
         int box_after = 0;
         bool keys_valid_after = false;
         bool ahead_after = false;
-        bool tile_valid_after[kBoxRing] = {false, false, false, false};
         int grid_sel_after = 0;
         int launches = 0;
     };
@@ -403,10 +397,8 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
                 CUDA_TRY(h, cudaMemset(h->tile_ring[k], 0, bytes));
             }
             h->tiles = true;
-            h->tile_want = h->tile_policy == 2;
-            CUDA_TRY(h, cudaMallocHost(&h->h_boxinfo, sizeof(GridBox)));
-            std::memset(h->h_boxinfo, 0, sizeof(GridBox));
-            CUDA_TRY(h, cudaEventCreateWithFlags(&h->boxinfo_ev, cudaEventDisableTiming));
+            CUDA_TRY(h, cudaMalloc(&h->d_tile_want, kBoxRing * sizeof(int)));
+            CUDA_TRY(h, cudaMemset(h->d_tile_want, 0, kBoxRing * sizeof(int)));
         }
     }
     CUDA_TRY(h, cudaMalloc(&h->d_box, kBoxRing * sizeof(GridBox)));
@@ -491,8 +483,7 @@ void nmpm_destroy(nmpm_handle h) {
     if (h->d_lame) cudaFree(h->d_lame);
     for (auto* t : h->tile_ring)
         if (t) cudaFree(t);
-    if (h->h_boxinfo) cudaFreeHost(h->h_boxinfo);
-    if (h->boxinfo_ev) cudaEventDestroy(h->boxinfo_ev);
+    if (h->d_tile_want) cudaFree(h->d_tile_want);
     if (h->d_box) cudaFree(h->d_box);
     if (h->d_box_partial) cudaFree(h->d_box_partial);
     if (h->d_error) cudaFree(h->d_error);
@@ -693,7 +684,17 @@ size_t nmpm_num_slots(nmpm_handle h) { return h ? h->n_store : 0; }
 int nmpm_key_tile_bits(nmpm_handle) { return kTileBits; }
 long long nmpm_launch_count(nmpm_handle h) { return h ? h->launches : 0; }
 int nmpm_fused(nmpm_handle h) { return h ? h->fuse : 0; }
-int nmpm_tiles_active(nmpm_handle h) { return (h && h->tile_want) ? 1 : 0; }
+int nmpm_tiles_active(nmpm_handle h) {  // synchronises: test / diagnostic hook
+    if (!h || !h->tiles) return 0;
+    int w = 0;
+    cudaSetDevice(h->device);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess ||
+        cudaMemcpy(&w, h->d_tile_want + h->box_cur, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return w;
+}
 
 int nmpm_lame(nmpm_handle h, float* mu_0, float* lambda_0) {
     if (!h) return NMPM_ERR_INVALID;
@@ -721,11 +722,15 @@ void* nmpm_get_stream(nmpm_handle h) { return h ? (void*) h->stream : nullptr; }
 // Active node tiles of the positions whose cell keys are `keys` (flags of ring slot `box`); see k_mark_tiles.
 // (Flags left in the slot by a replaced state are only a superset.)
 static void mark_tiles(nmpm_sim* h, const uint32_t* keys, uint32_t n, int box) {
-    h->tile_valid[box] = h->tile_want;
-    if (!h->tile_want || n == 0) return;
+    if (!h->tiles) return;
+    // decide for these positions (hysteresis against the previous slot's decision), then raise the flags if wanted
+    k_tile_decide<<<1, 32, 0, h->stream>>>(h->d_box + box, n, h->P.n1, h->d_tile_want + (box + kBoxRing - 1) % kBoxRing,
+                                           h->d_tile_want + box, h->tile_policy);
+    h->launches++;
+    if (n == 0) return;
     const unsigned per_block = kMarkWarps * kMarkKeysPerWarp;
     k_mark_tiles<<<(n + per_block - 1) / per_block, kMarkWarps * 32, 0, h->stream>>>(keys, n, h->tile_ring[box],
-                                                                                    (h->P.n1 + 3) >> 2);
+                                                                                    (h->P.n1 + 3) >> 2, h->d_tile_want + box);
     h->launches++;
 }
 
@@ -785,13 +790,13 @@ static int ensure_box(nmpm_sim* h) {
 // zero what the P2G of the positions of box `box` scattered into `grid`: their flagged tiles (lowering the flags), or the
 // node box itself
 static void clear_grid(nmpm_sim* h, float4* grid, int box) {
-    if (h->tile_valid[box]) {
-        k_tiles3<0><<<kBoxBlocks, 256, 0, h->stream>>>(grid, h->tile_ring[box], h->P);
-        h->tile_valid[box] = false;  // lowered
-    } else {
-        NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(grid, h->d_box + box, h->P.n1,
-                                                                                h->scenes > 1 ? h->scenes * h->P.n1 : 0)));
+    const int* want = h->tiles ? h->d_tile_want + box : nullptr;
+    if (want) {
+        k_tiles3<0><<<kBoxBlocks, 256, 0, h->stream>>>(grid, h->tile_ring[box], h->P, want);
+        h->launches++;
     }
+    NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(grid, h->d_box + box, h->P.n1,
+                                                                            h->scenes > 1 ? h->scenes * h->P.n1 : 0, want)));
     h->launches++;
 }
 
@@ -858,11 +863,12 @@ static int do_p2g(nmpm_sim* h) {
 }
 
 static int do_grid_op(nmpm_sim* h) {
-    if (h->tile_valid[h->box_cur]) {
-        k_tiles3<1><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->tile_ring[h->box_cur], h->P);
-    } else {
-        NMPM_DISPATCH_DIM(h, (k_grid_op<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + h->box_cur, h->P)));
+    const int* want = h->tiles ? h->d_tile_want + h->box_cur : nullptr;
+    if (want) {
+        k_tiles3<1><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->tile_ring[h->box_cur], h->P, want);
+        h->launches++;
     }
+    NMPM_DISPATCH_DIM(h, (k_grid_op<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + h->box_cur, h->P, want)));
     h->launches++;
     return NMPM_OK;
 }
@@ -871,8 +877,8 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
     if (h->n == 0) {
         h->n_store = 0;
         h->box_cur = (h->box_cur + 1) % kBoxRing;
-        h->tile_valid[h->box_cur] = false;
         k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + h->box_cur);
+        if (h->tiles) CUDA_TRY(h, cudaMemsetAsync(h->d_tile_want + h->box_cur, 0, sizeof(int), h->stream));
         // an empty slab: its key array is all "gone" marks, and stays aligned with the slots as particles arrive —
         // no key pass may ever run over the (uninitialised) store
         if (h->slab) h->keys_valid = true;
@@ -885,7 +891,7 @@ static int do_g2p(nmpm_sim* h, const MigrateArgs& mig = MigrateArgs{0, 0, nullpt
     const bool next_sorts = h->opt.sort_every > 0 && ((h->steps_done + 1) % h->opt.sort_every) == 0;
     // a slab keeps the key array aligned with the slots at all times: it carries the "migrated away" marks
     // (and in tile mode: the active node tiles of the coming step are raised from them, mark_tiles below)
-    uint32_t* keys_out = (next_sorts || h->slab || h->tile_want) ? h->sort.keys_a : nullptr;
+    uint32_t* keys_out = (next_sorts || h->slab || h->tiles) ? h->sort.keys_a : nullptr;
     const uint32_t* gone_keys = (h->dev_counts || (h->slab && !h->perm && h->n_gone)) ? h->sort.keys_a : nullptr;
     const int box_next = (h->box_cur + 1) % kBoxRing;
     k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + box_next);
@@ -1032,10 +1038,7 @@ static int graph_steps(nmpm_sim* h, int count) {
     const int gsel0 = h->grid_sel;
     const int key = h->cur | (h->keys_valid ? 2 : 0) | (box0 << 2) | (boxv0 ? 16 : 0) |
                     ((se > 0 ? (int) (h->steps_done % se) : 0) << 5) | (count << 12) | (ahead0 ? 1 << 20 : 0) | (gsel0 << 21) |
-                    ((h->fuse == 1 && h->steps_done == 0) ? 1 << 22 : 0) | (h->tile_want ? 1 << 23 : 0) |
-                    (h->tile_valid[0] ? 1 << 24 : 0) | (h->tile_valid[1] ? 1 << 25 : 0) | (h->tile_valid[2] ? 1 << 26 : 0) |
-                    (h->tile_valid[3] ? 1 << 27 : 0);
-    const bool tv0[kBoxRing] = {h->tile_valid[0], h->tile_valid[1], h->tile_valid[2], h->tile_valid[3]};
+                    ((h->fuse == 1 && h->steps_done == 0) ? 1 << 22 : 0);
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
         if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
@@ -1066,14 +1069,12 @@ static int graph_steps(nmpm_sim* h, int count) {
             h->perm = nullptr;
             if (h->grid_sel != gsel0) std::swap(h->grid, h->grid_alt), h->grid_sel = gsel0;
             h->p2g_ahead = ahead0;
-            for (int k = 0; k < kBoxRing; ++k) h->tile_valid[k] = tv0[k];
             return graph_steps(h, count);
         }
         sg.cur_after = h->cur;
         sg.keys_valid_after = h->keys_valid;
         sg.box_after = h->box_cur;
         sg.ahead_after = h->p2g_ahead;
-        for (int k = 0; k < kBoxRing; ++k) sg.tile_valid_after[k] = h->tile_valid[k];
         sg.grid_sel_after = h->grid_sel;
         sg.launches = (int) (h->launches - l0);
         it = h->graphs.emplace(key, sg).first;
@@ -1088,42 +1089,10 @@ static int graph_steps(nmpm_sim* h, int count) {
     h->perm = nullptr;
     h->grid_valid = true;
     h->p2g_ahead = it->second.ahead_after;
-    for (int k = 0; k < kBoxRing; ++k) h->tile_valid[k] = it->second.tile_valid_after[k];
     if (h->grid_sel != it->second.grid_sel_after) std::swap(h->grid, h->grid_alt), h->grid_sel = it->second.grid_sel_after;
     h->steps_done += count;
     h->launches += it->second.launches;
     return NMPM_OK;
-}
-
-// Adaptive tile mode: the node box of a recent step travels to pinned memory behind the steps (no host wait); the next
-// call looks at it if it has landed.  Tiles pay when the box is mostly empty: wanted above 1.5 nodes per particle (a
-// compact 8-per-cell block has ~0.4), dropped again below 1.0.
-static void post_boxinfo(nmpm_sim* h) {
-    if (!h->tiles || h->tile_policy != 0 || h->boxinfo_pending || !h->box_valid) return;
-    if (cudaMemcpyAsync(h->h_boxinfo, h->d_box + h->box_cur, sizeof(GridBox), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
-        cudaEventRecord(h->boxinfo_ev, h->stream) != cudaSuccess) {
-        cudaGetLastError();
-        return;
-    }
-    h->boxinfo_pending = true;
-}
-static void update_tile_want(nmpm_sim* h) {
-    if (!h->tiles || h->tile_policy != 0 || !h->boxinfo_pending) return;
-    if (cudaEventQuery(h->boxinfo_ev) != cudaSuccess) {
-        cudaGetLastError();
-        return;  // still in flight: decide later
-    }
-    h->boxinfo_pending = false;
-    const GridBox* b = reinterpret_cast<const GridBox*>(h->h_boxinfo);
-    double vol = 1.0;
-    for (int d = 0; d < 3; ++d) {
-        const int lo = b->lo[d] < 0 ? 0 : b->lo[d], hi = (b->hi[d] + 2 > h->P.n1 - 1) ? h->P.n1 - 1 : b->hi[d] + 2;
-        vol *= hi >= lo ? (double) (hi - lo + 1) : 0.0;
-    }
-    const double per_particle = h->n ? vol / (double) h->n : 0.0;
-    if (!h->tile_want && per_particle > 1.5) h->tile_want = true;
-    else if (h->tile_want && per_particle < 1.0)
-        h->tile_want = false;
 }
 
 // host states repeat with this period (sort cadence x store parity, node-box ring)
@@ -1149,12 +1118,10 @@ int nmpm_advance(nmpm_handle h, int nsteps) {
     if (int rc = poll_error(h)) return rc;
     const int cyc = graph_cycle(h);
     for (int s = 0; s < nsteps;) {
-        update_tile_want(h);
         // whole cycles in one graph once the state is periodic (keys and box valid: i.e. not the very first step)
         const int k = (nsteps - s >= cyc && cyc <= 64 && h->steps_done >= cyc && h->steps_done % cyc == 0) ? cyc : 1;
         if (int rc = graph_steps(h, k)) return rc;
         s += k;
-        post_boxinfo(h);
     }
     CUDA_TRY(h, cudaMemcpyAsync(h->h_error, h->d_error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     return NMPM_OK;

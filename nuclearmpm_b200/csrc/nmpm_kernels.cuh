@@ -192,7 +192,8 @@ __device__ __forceinline__ size_t box_node(uint32_t i, const int (&lo)[D], const
 // ---- K1: clear the nodes the previous P2G wrote (grid-stride over the previous box) ----------
 template <int D>
 __global__ void __launch_bounds__(256) k_clear_box(float4* __restrict__ grid, const GridBox* __restrict__ box, int n1,
-                                                   int n1x = 0) {
+                                                   int n1x = 0, const int* __restrict__ tiles_instead = nullptr) {
+    if (tiles_instead && *tiles_instead) return;  // k_tiles3<0> clears these positions' nodes
     int lo[D], c[D];
     uint32_t ext[D];
     const uint32_t vol = box_extent<D>(box, n1, lo, ext, n1x);
@@ -225,6 +226,30 @@ __device__ __forceinline__ int node_tiles_per_axis(int n1) { return (n1 + 3) >> 
 // {tile, corners} in a private 32-entry table in shared memory; what it holds at the end goes to memory once (test through
 // L1, then a 32-bit RED.OR).  (x & 3) >= 2 is bit 1 of the 2-bit cell coordinate: key bits 5, 3, 1.
 // The kernel streams 4 B per particle.
+// Tile mode is decided on the DEVICE, per step, from the node box of the coming step's positions (so that a host that
+// enqueues thousands of steps ahead still gets the switch at the right step): tiles pay when the box is mostly empty —
+// wanted above 1.5 box nodes per particle (a compact 8-per-cell block has ~0.4, cfg4 at step 150 has 2.2 and 76 % of its
+// box empty), dropped again below 1.0.  want[b] belongs to ring slot b like box[b] and the flag array b; every consumer
+// (k_mark_tiles, k_tiles3 / k_clear_box, k_grid_op) reads it and returns at once if it is not its turn.
+__global__ void k_tile_decide(const GridBox* __restrict__ box, uint32_t n, int n1, const int* __restrict__ want_prev,
+                              int* __restrict__ want_out, int policy) {
+    if (threadIdx.x != 0) return;
+    int w = policy == 2 ? 1 : 0;
+    if (policy == 0) {
+        float vol = 1.0f;
+        for (int d = 0; d < 3; ++d) {
+            const int lo = max(box->lo[d], 0), hi = min(box->hi[d] + 2, n1 - 1);
+            vol *= hi >= lo ? (float) (hi - lo + 1) : 0.0f;
+        }
+        const float per_particle = n ? vol / (float) n : 0.0f;
+        w = *want_prev;
+        if (!w && per_particle > 1.5f) w = 1;
+        else if (w && per_particle < 1.0f)
+            w = 0;
+    }
+    *want_out = w;
+}
+
 constexpr int kMarkWarps = 8, kMarkKeysPerWarp = 1024;
 __device__ __forceinline__ void tile_raise(uint32_t* __restrict__ flags, uint32_t lo, unsigned corners, int T) {
     unsigned up = 0u;  // all tests first (through L1: a stale 0 only costs a redundant reduction), then the reductions
@@ -243,7 +268,9 @@ __device__ __forceinline__ void tile_raise(uint32_t* __restrict__ flags, uint32_
         }
 }
 __global__ void __launch_bounds__(kMarkWarps * 32) k_mark_tiles(const uint32_t* __restrict__ keys, uint32_t n,
-                                                                uint32_t* __restrict__ flags, int T) {
+                                                                uint32_t* __restrict__ flags, int T,
+                                                                const int* __restrict__ want) {
+    if (*want == 0) return;  // the coming step works on its node box (k_tile_decide)
     // per warp: 32 entries {tile, corners to raise}; an entry is claimed by the first tile that hashes to it and never
     // evicted (a tile that finds its entry taken goes to memory directly), the warp flushes its entries once at the end —
     // so the walk itself waits for no global memory access except the key loads
@@ -291,7 +318,9 @@ __global__ void __launch_bounds__(kMarkWarps * 32) k_mark_tiles(const uint32_t* 
 template <int D>
 __device__ __forceinline__ bool grid_op_value(float4& g, const int (&c)[D], const MaterialParams& P);
 template <int OP>
-__global__ void __launch_bounds__(256) k_tiles3(float4* __restrict__ grid, uint32_t* __restrict__ flags, MaterialParams P) {
+__global__ void __launch_bounds__(256) k_tiles3(float4* __restrict__ grid, uint32_t* __restrict__ flags, MaterialParams P,
+                                                const int* __restrict__ want) {
+    if (*want == 0) return;  // these positions were not flagged: the node-box kernel does the work
     constexpr int U = 4;  // flagged tiles in flight per warp (their loads are issued together)
     const int n1 = P.n1, T = node_tiles_per_axis(n1);
     const uint32_t nwords = ((uint32_t) (T * T * T) + 31u) >> 5;
@@ -532,7 +561,8 @@ __device__ __forceinline__ void grid_op_node(float4* __restrict__ cell, const in
 // grid-stride over the node box of the current particles (see GridBox)
 template <int D>
 __global__ void __launch_bounds__(256) k_grid_op(float4* __restrict__ grid, const GridBox* __restrict__ box,
-                                                 MaterialParams P) {
+                                                 MaterialParams P, const int* __restrict__ tiles_instead = nullptr) {
+    if (tiles_instead && *tiles_instead) return;  // k_tiles3<1> updates these positions' nodes
     int lo[D], c[D];
     uint32_t ext[D];
     const uint32_t vol = box_extent<D>(box, P.n1, lo, ext, P.scenes > 1 ? P.scenes * P.n1 : 0);

@@ -28,13 +28,15 @@ a = ap.parse_args()
 exe = build_cli.build()
 N = 2 * 25 * 25  # --cubes 2 --cube-res 25
 out = {}
-for tag, steps, dump in (("no_dump", a.steps, False), ("dump", a.dump_steps, True)):
+# batched (the default: scenes of one model in ONE simulation) and, for comparison, one simulation per scene
+for tag, steps, dump, batch in (("no_dump", a.steps, False, "1"), ("dump", a.dump_steps, True, "1"),
+                                ("no_dump_per_scene_sims", a.steps, False, "0")):
     tmp = Path(tempfile.mkdtemp(prefix="nmpm_cfg5_"))
     (tmp / "scenes.txt").write_text("\n".join(make_scenes.scene_flags(s, steps, dump) for s in range(a.scenes)) + "\n")
     t0 = time.perf_counter()
     import os
     r = subprocess.run([str(exe), "--scenes", str(tmp / "scenes.txt"), "--out-dir", str(tmp / "out")], capture_output=True,
-                       text=True, cwd=tmp, env=dict(os.environ, NMPM_CLI_TIMING="1"))
+                       text=True, cwd=tmp, env=dict(os.environ, NMPM_CLI_TIMING="1", NMPM_CLI_BATCH=batch))
     dt = time.perf_counter() - t0
     inner = {}
     for ln in r.stderr.splitlines():
@@ -43,7 +45,7 @@ for tag, steps, dump in (("no_dump", a.steps, False), ("dump", a.dump_steps, Tru
     if r.returncode != 0:
         raise SystemExit(f"{tag}: CLI failed: {r.stderr[-500:]}")
     files = sum(1 for _ in (tmp / "out").rglob("*.txt")) if dump else 0
-    out[tag] = {"scenes": a.scenes, "particles_per_scene": N, "steps": steps, "wall_s": dt,
+    out[tag] = {"batched": batch == "1", "scenes": a.scenes, "particles_per_scene": N, "steps": steps, "wall_s": dt,
                 "value": a.scenes * N * steps / dt, "unit": "particle-steps/s", "snapshot_files": files,
                 "setup_s": inner.get("setup_s"), "run_s": inner.get("run_s"),
                 "value_stepping_only": (a.scenes * N * steps / inner["run_s"]) if inner.get("run_s") else None,
