@@ -313,8 +313,8 @@ __global__ void __launch_bounds__(kMarkWarps * 32) k_mark_tiles(const uint32_t* 
     if (mine) tile_raise(flags, tag[warp][lane], mine, T);
 }
 
-// One warp per flag word (32 consecutive tiles): the warp visits every flagged tile — lane -> (row, half): 16 (x,y) rows
-// of 4 z-contiguous nodes, two nodes (32 B) per lane.  OP 0: zero the nodes and lower the flags; OP 1: grid_op.
+// One warp per flag word (32 consecutive tiles): the warp visits every flagged tile — 16 (x,y) rows of 4 z-contiguous
+// nodes, a lane pair per row, two nodes per lane (z and z + 2).  OP 0: zero the nodes and lower the flags; OP 1: grid_op.
 template <int D>
 __device__ __forceinline__ bool grid_op_value(float4& g, const int (&c)[D], const MaterialParams& P);
 template <int OP>
@@ -326,7 +326,9 @@ __global__ void __launch_bounds__(256) k_tiles3(float4* __restrict__ grid, uint3
     const uint32_t nwords = ((uint32_t) (T * T * T) + 31u) >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int row = lane & 15, half = lane >> 4;
+    // lane -> (row, half): a lane pair covers two z-adjacent nodes, so that every load / store instruction of the warp
+    // moves whole 32-byte sectors (half-filled sectors are read-modify-write at the L2)
+    const int row = lane >> 1, half = lane & 1;
     for (uint32_t w = warp; w < nwords; w += nwarps) {
         unsigned active = flags[w];
         if (active == 0u) continue;
@@ -345,10 +347,10 @@ __global__ void __launch_bounds__(256) k_tiles3(float4* __restrict__ grid, uint3
                     active &= active - 1u;
                     const uint32_t q = t / (uint32_t) T;
                     const int tz = (int) (t - q * (uint32_t) T), ty = (int) (q % (uint32_t) T), tx = (int) (q / (uint32_t) T);
-                    c[u][0] = 4 * tx + (row >> 2), c[u][1] = 4 * ty + (row & 3), c[u][2] = 4 * tz + 2 * half;
+                    c[u][0] = 4 * tx + (row >> 2), c[u][1] = 4 * ty + (row & 3), c[u][2] = 4 * tz + half;  // and z + 2
                     if (c[u][0] < n1 && c[u][1] < n1) {
                         node[u] = grid + ((size_t) (c[u][0] * n1 + c[u][1]) * n1 + c[u][2]);
-                        ok[u][0] = c[u][2] < n1, ok[u][1] = c[u][2] + 1 < n1;
+                        ok[u][0] = c[u][2] < n1, ok[u][1] = c[u][2] + 2 < n1;
                     }
                 }
             }
@@ -357,20 +359,20 @@ __global__ void __launch_bounds__(256) k_tiles3(float4* __restrict__ grid, uint3
                 for (int u = 0; u < U; ++u)
 #pragma unroll
                     for (int e = 0; e < 2; ++e)
-                        if (ok[u][e]) node[u][e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        if (ok[u][e]) node[u][2 * e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             } else {
                 float4 g[U][2];
 #pragma unroll
                 for (int u = 0; u < U; ++u)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) g[u][e] = ok[u][e] ? node[u][e] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    for (int e = 0; e < 2; ++e) g[u][e] = ok[u][e] ? node[u][2 * e] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
                 for (int u = 0; u < U; ++u)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         if (!ok[u][e]) continue;
-                        const int cc[3] = {c[u][0], c[u][1], c[u][2] + e};
-                        if (grid_op_value<3>(g[u][e], cc, P)) node[u][e] = g[u][e];
+                        const int cc[3] = {c[u][0], c[u][1], c[u][2] + 2 * e};
+                        if (grid_op_value<3>(g[u][e], cc, P)) node[u][2 * e] = g[u][e];
                     }
             }
         }
