@@ -266,8 +266,21 @@ def run_gpu(args):
     # advance() replays one CUDA graph per host-side step state (2 * sort_every of them): run through the cycle once
     # so that no capture / instantiation lands in the warm-up or in the timed region
     # (and the 8-step cycle graph nmpm_advance uses for runs of steps: 4 cycles in one call capture it)
-    prime = 0  # (graphs are captured by the untimed calls at the top of timed_window)
+    # advance() replays CUDA graphs: one per host-side step state for single steps (8 states at the default cadence) and one
+    # for a whole 8-step cycle.  Capture them all before anything is timed: W warm-up steps, single steps up to the next
+    # cycle boundary, two whole cycles (capture + replay), then one cycle of single steps.
     sim.advance(args.warmup)
+    cyc = step = 2 * args.sort_every if args.sort_every > 0 else 1   # nmpm_api.cu: graph_cycle()
+    while cyc % 4:
+        cyc += step
+    prime = 0
+    while (args.warmup + prime) % cyc:
+        sim.advance(1)
+        prime += 1
+    sim.advance(cyc), sim.advance(cyc)
+    for _ in range(cyc):
+        sim.advance(1)
+    prime += 3 * cyc
     sync()
     peak, peak_src = measured_peak_gbs()
     ab = ALGO_BYTES[dim]
@@ -277,12 +290,6 @@ def run_gpu(args):
         """K steps between CUDA events on the sim's stream, then a separate per-phase pass (events per phase
         serialise the step, so it is not part of the timed region)."""
         nonlocal steps_done
-        # two untimed calls of the same length first: advance(n) replays graphs whose shape depends on where the call
-        # starts in the 8-step cycle (and on the adaptive tile mode); the start positions of calls of one length alternate
-        # between at most two alignments, so after two calls every graph of the timed call exists
-        sim.advance(args.steps)
-        sim.advance(args.steps)
-        steps_done += 2 * args.steps
         first = steps_done
         l0 = sim.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
