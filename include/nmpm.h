@@ -72,8 +72,10 @@ typedef struct nmpm_options {
                          overrides.  Results: same sums in a different floating-point order (like any sort cadence) */
     int tiles;        /* 3D, single GPU: grid_op and the grid clear visit only the 4^3-node tiles that stencils cover (one flag
                          bit per tile, raised together with the node box) instead of the particles' whole bounding box.
-                         0 = adaptive (on while the box holds more than ~1.5 nodes per particle, i.e. a dispersed scene),
-                         1 = never, 2 = always.  Env NMPM_TILES=0/1/2 (= never / adaptive / always) overrides.  Same results */
+                         0 = auto: adaptive on grids of 8 Mi nodes and more (decided on the device per step: on while the
+                         box holds more than ~1.5 nodes per particle, i.e. a dispersed scene), never on smaller grids,
+                         1 = never, 2 = always, 3 = adaptive whatever the grid size.
+                         Env NMPM_TILES=0/1/2/3 (= never / auto / always / adaptive) overrides.  Same results */
     int reserved[6];
 } nmpm_options;
 

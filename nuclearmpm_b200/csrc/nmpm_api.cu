@@ -389,7 +389,12 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
     }
     if (dim == 3 && !h->slab) {
         h->tile_policy = h->opt.tiles;
-        if (const char* tl = std::getenv("NMPM_TILES")) h->tile_policy = (*tl == '0') ? 1 : (*tl == '2') ? 2 : 0;
+        if (const char* tl = std::getenv("NMPM_TILES")) h->tile_policy = (*tl == '0') ? 1 : (*tl == '2') ? 2 : (*tl == '3') ? 3 : 0;
+        // adaptive: only where the dense grid is large enough for its bounding box to cost anything (cfg2 / snow128 at
+        // res 128 clear + update their whole 2 M-node grid in 0.03 ms; the five extra near-empty launches per step of the
+        // tile machinery cost a launch-bound 262 k-particle scene 8 %)
+        if (h->tile_policy == 0 && h->cells < ((size_t) 8 << 20)) h->tile_policy = 1;
+        if (h->tile_policy == 3) h->tile_policy = 0;  // adaptive whatever the grid size (tests)
         if (h->tile_policy != 1) {
             const size_t T = (n1 + 3) / 4, bytes = ((T * T * T + 31) / 32 + 16) * sizeof(uint32_t);
             for (int k = 0; k < kBoxRing; ++k) {
@@ -798,6 +803,21 @@ static void clear_grid(nmpm_sim* h, float4* grid, int box) {
     NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(grid, h->d_box + box, h->P.n1,
                                                                             h->scenes > 1 ? h->scenes * h->P.n1 : 0, want)));
     h->launches++;
+}
+
+// An out-of-grid particle scatters to clamped nodes that neither its key (kKeyOutOfGrid) nor, in tile mode, any flag
+// accounts for.  The step is flagged and the state is void, but the caller may upload a repaired state into the same
+// handle: start it from dense zero grids and lowered flags.
+static void reset_grids_after_error(nmpm_sim* h) {
+    if (!h->tiles || !(h->error_latched || (h->h_error && *((volatile int*) h->h_error) != 0))) return;
+    const size_t T = ((size_t) h->P.n1 + 3) / 4, words = (T * T * T + 31) / 32;
+    cudaMemsetAsync(h->grid, 0, h->cells * sizeof(float4), h->stream);
+    if (h->grid_alt) cudaMemsetAsync(h->grid_alt, 0, h->cells * sizeof(float4), h->stream);
+    for (auto* t : h->tile_ring) cudaMemsetAsync(t, 0, words * sizeof(uint32_t), h->stream);
+    cudaMemsetAsync(h->d_tile_want, 0, kBoxRing * sizeof(int), h->stream);
+    for (int k = 0; k < kBoxRing; ++k) k_box_reset<<<1, 32, 0, h->stream>>>(h->d_box + k);
+    h->p2g_ahead = false;
+    h->box_valid = false;
 }
 
 // The particle state is about to be replaced (upload): the sums the last fused G2P scattered ahead into grid_alt belong to
@@ -1266,6 +1286,7 @@ int nmpm_upload_particles(nmpm_handle h, const float* x, const float* v, const f
     CUDA_TRY(h, e);
     ParticleStore& S = h->store[h->cur];
     ParticleStore& T = h->store[h->cur ^ 1];
+    reset_grids_after_error(h);
     discard_p2g_ahead(h);
     if (h->phase_next != 0) {
         // Upload in the middle of a step (after nmpm_phase(P2G) or (GRID_OP)): the aborted step's P2G has already
@@ -1344,6 +1365,7 @@ int nmpm_upload_particles_async(nmpm_handle h, const float* x, const float* v, c
     CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->io.in_ready[b], 0));
     ParticleStore& S = h->store[h->cur];
     ParticleStore& T = h->store[h->cur ^ 1];
+    reset_grids_after_error(h);
     discard_p2g_ahead(h);
     if (h->phase_next != 0) clear_grid(h, h->grid, h->box_cur);  // see nmpm_upload_particles
     NMPM_DISPATCH_DIM(h, (k_restore_constants<D><<<blocks_for(n, 256), 256, 0, h->stream>>>(S, T, (uint32_t) n)));

@@ -11,7 +11,7 @@ from test_parity_gpu import FIELDS, MODELS, check_grid, check_state
 
 pytestmark = pytest.mark.gpu
 
-ADAPTIVE, NEVER, ALWAYS = 0, 1, 2
+AUTO, NEVER, ALWAYS, ADAPTIVE = 0, 1, 2, 3   # nmpm_options.tiles
 
 
 def scene(seed, n=6000, lo=0.25, hi=0.75):
@@ -63,7 +63,7 @@ def test_adaptive_policy_switches_on_for_a_dispersed_scene_and_off_for_a_block()
     rng = np.random.default_rng(77)
     x = rng.uniform(0.1, 0.9, (20000, 3)).astype(np.float32)
     v = rng.normal(0, 1, x.shape).astype(np.float32)
-    auto = nm.MPMSimulation(x, co.JELLY, 64, v=v)
+    auto = nm.MPMSimulation(x, co.JELLY, 64, v=v, tiles=ADAPTIVE)
     boxed = nm.MPMSimulation(x, co.JELLY, 64, v=v, tiles=NEVER)
     cpu = co.CpuSim(x, co.JELLY, 64, v=v)
     assert not auto.tiles_active
@@ -73,10 +73,13 @@ def test_adaptive_policy_switches_on_for_a_dispersed_scene_and_off_for_a_block()
     check_state(auto.particles(), boxed.particles(), "adaptive vs box", scale=40.0)
     check_state(auto.particles(), cpu.particles(), "adaptive vs oracle", scale=40.0)
     check_grid(*auto.grid(), *cpu.grid(), "adaptive grid", scale=40.0)
-    block = nm.MPMSimulation(nm.cube(3, 40, 0.3, 0.6), co.SNOW, 64)
+    block = nm.MPMSimulation(nm.cube(3, 40, 0.3, 0.6), co.SNOW, 64, tiles=ADAPTIVE)
     for k in (1, 1, 4, 8):
         block.advance(k, sync=True)
     assert not block.tiles_active
+    small = nm.MPMSimulation(x, co.JELLY, 64, v=v)           # auto: a 65^3 grid never pays for the tile machinery
+    small.advance(3, sync=True)
+    assert not small.tiles_active
 
 
 def test_mode_switch_in_both_directions_keeps_the_grid_clean():
@@ -86,7 +89,7 @@ def test_mode_switch_in_both_directions_keeps_the_grid_clean():
     n = 8000
     compact = rng.uniform(0.45, 0.55, (n, 3)).astype(np.float32)       # 10^3 nodes: far below 1 node per particle
     spread = rng.uniform(0.1, 0.9, (n, 3)).astype(np.float32)         # 50^3 nodes
-    sim = nm.MPMSimulation(compact, co.LIQUID, 64)
+    sim = nm.MPMSimulation(compact, co.LIQUID, 64, tiles=ADAPTIVE)
     for phase, x in enumerate([spread, compact, spread, compact]):
         z = np.zeros((n, 3), np.float32)
         eye = np.tile(np.eye(3, dtype=np.float32), (n, 1, 1))
@@ -97,3 +100,27 @@ def test_mode_switch_in_both_directions_keeps_the_grid_clean():
             check_grid(*sim.grid(), *cpu.grid(), f"phase {phase}", scale=10.0)
         assert sim.tiles_active == (phase % 2 == 0), f"phase {phase}: tiles_active = {sim.tiles_active}"
         check_state(sim.particles(), cpu.particles(), f"phase {phase}", scale=10.0)
+
+
+def test_repaired_state_after_an_out_of_grid_error_starts_from_clean_grids():
+    """An out-of-grid particle scatters to clamped nodes that no tile flag covers (its key is "out of grid").  The step
+    fails; uploading a repaired state into the same handle must not inherit those sums."""
+    x, v = scene(530, 3000)
+    sim = nm.MPMSimulation(x, co.JELLY, 48, v=v, tiles=ALWAYS)
+    sim.advance(2, sync=True)
+    bad = sim.particles()
+    bad["x"][11] = (0.999, 0.5, 0.5)
+    sim.upload(*[bad[k] for k in FIELDS])
+    with pytest.raises(nm.OutOfGridError):
+        sim.advance(2, sync=True)
+    z = np.zeros_like(x)
+    sim.upload(x, v, np.tile(np.eye(3, dtype=np.float32), (len(x), 1, 1)), np.zeros((len(x), 3, 3), np.float32),
+               np.ones(len(x), np.float32))
+    cpu = co.CpuSim(x, co.JELLY, 48, v=v)
+    for step in range(3):
+        sim.advance(1, sync=True), cpu.advance(1)
+        ref = cpu.particles()
+        check_grid(*sim.grid(), *cpu.grid(), f"grid {step + 1} steps after the repaired upload", scale=2.0)
+        check_state(sim.particles(), ref, f"state {step + 1} steps after the repaired upload", scale=2.0)
+        assert np.array_equal(sim.grid()[1] != 0, cpu.grid()[1] != 0), "stale nodes survived the error"
+        sim.upload(*[ref[k] for k in FIELDS])     # teacher-forced: node velocities of tiny masses amplify any drift
