@@ -8,7 +8,10 @@
 // Per pass (3 kernels):
 //   sort_hist    : per-tile digit histogram (shared-memory integer atomics)  -> hist[digit][tile]
 //   sort_scan    : one CTA per digit scans its row over tiles; the last CTA to finish scans the
-//                  256 digit totals (threadfence + counter) -> digit_base
+//                  digit totals (threadfence + counter) -> digit_base
+// Digit width (NMPM_RADIX_BITS): 10-bit digits sort cfg4's 28-bit keys (+1 bit for the special keys) in 3 passes instead
+// of 4, but every pass is slower (1 024 scan rows, 32-byte instead of 64-byte runs in the scatter): measured 0.76 against
+// 0.71 ms per 16.8 M pairs on cfg4 and 0.110 against 0.122 ms on cfg3 (gpurun r3q) — 8 stays.
 //   sort_scatter : warp-synchronous stable ranking (__match_any_sync) + scatter
 // Integer atomics only: the result is deterministic.
 #pragma once
@@ -20,24 +23,31 @@ namespace nmpm {
 constexpr int kSortThreads = 256;
 constexpr int kSortItems = 16;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per CTA
-constexpr int kRadix = 256;
+#ifndef NMPM_RADIX_BITS
+#define NMPM_RADIX_BITS 8
+#endif
+constexpr int kRadixBits = NMPM_RADIX_BITS;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr uint32_t kRadixMask = kRadix - 1;
 
 __global__ void __launch_bounds__(kSortThreads) sort_hist(const uint32_t* __restrict__ keys, uint32_t n, int shift,
                                                           uint32_t* __restrict__ hist, uint32_t ntiles) {
     __shared__ uint32_t h[kRadix];
-    h[threadIdx.x] = 0;
+    for (int d = threadIdx.x; d < kRadix; d += kSortThreads) h[d] = 0;
     __syncthreads();
     const uint32_t start = blockIdx.x * kSortTile;
+    // (plain shared-memory atomics: aggregating the lanes of equal digit with __match_any_sync first — cell-sorted keys
+    // repeat their digit ~8 times in a row — was measured slower, 0.184 against 0.178 ms of sort per step, gpurun r3r)
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
         const uint32_t idx = start + i * kSortThreads + threadIdx.x;
-        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 0xFFu], 1u);
+        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & kRadixMask], 1u);
     }
     __syncthreads();
-    hist[threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+    for (int d = threadIdx.x; d < kRadix; d += kSortThreads) hist[(size_t) d * ntiles + blockIdx.x] = h[d];
 }
 
-// grid = 256 CTAs (one per digit).  Exclusive scan of hist[d][0..ntiles) in place; row totals to
+// grid = kRadix CTAs (one per digit).  Exclusive scan of hist[d][0..ntiles) in place; row totals to
 // digit_total; the last CTA done turns digit_total into the exclusive digit_base.
 __global__ void __launch_bounds__(256) sort_scan(uint32_t* __restrict__ hist, uint32_t ntiles,
                                                  uint32_t* __restrict__ digit_total, uint32_t* __restrict__ digit_base,
@@ -79,8 +89,15 @@ __global__ void __launch_bounds__(256) sort_scan(uint32_t* __restrict__ hist, ui
     __syncthreads();
     if (is_last) {
         __threadfence();
-        const uint32_t v = ((volatile uint32_t*) digit_total)[threadIdx.x];
-        uint32_t incl = v;
+        // exclusive scan of the kRadix digit totals: kRadix / 256 consecutive digits per thread
+        constexpr int PER = kRadix / 256;
+        uint32_t v[PER], sum = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            v[q] = ((volatile uint32_t*) digit_total)[threadIdx.x * PER + q];
+            sum += v[q];
+        }
+        uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -92,7 +109,12 @@ __global__ void __launch_bounds__(256) sort_scan(uint32_t* __restrict__ hist, ui
 #pragma unroll
         for (int w = 0; w < 8; ++w)
             if (w < warp) woff += warp_sums[w];
-        digit_base[threadIdx.x] = woff + incl - v;
+        uint32_t run = woff + incl - sum;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            digit_base[threadIdx.x * PER + q] = run;
+            run += v[q];
+        }
         if (threadIdx.x == 0) *done_counter = 0;  // re-arm for the next pass
     }
 }
@@ -121,9 +143,9 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __r
         const bool valid = idx < n;
         key[i] = valid ? keys_in[idx] : 0xFFFFFFFFu;
         val[i] = valid ? (vals_in ? vals_in[idx] : idx) : 0u;
-        const uint32_t digit = (key[i] >> shift) & 0xFFu;
+        const uint32_t digit = (key[i] >> shift) & kRadixMask;
         // invalid lanes get a private pseudo-digit so that they match nobody
-        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : (0x100u | (uint32_t) lane));
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : ((uint32_t) kRadix | (uint32_t) lane));
         const uint32_t before = warp_cnt[warp][digit];
         rank[i] = (uint16_t) (before + __popc(peers & lt_mask));
         __syncwarp();
@@ -131,8 +153,8 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __r
         __syncwarp();
     }
     __syncthreads();
-    {   // exclusive prefix over warps per digit, seeded with the global base of (digit, tile)
-        const int d = threadIdx.x;
+    for (int d = threadIdx.x; d < kRadix; d += kSortThreads) {
+        // exclusive prefix over warps per digit, seeded with the global base of (digit, tile)
         uint32_t run = digit_base[d] + hist[(size_t) d * ntiles + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
@@ -146,7 +168,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __r
     for (int i = 0; i < kSortItems; ++i) {
         const uint32_t idx = wstart + i * 32 + lane;
         if (idx < n) {
-            const uint32_t pos = warp_cnt[warp][(key[i] >> shift) & 0xFFu] + rank[i];
+            const uint32_t pos = warp_cnt[warp][(key[i] >> shift) & kRadixMask] + rank[i];
             keys_out[pos] = key[i];
             vals_out[pos] = val[i];
         }
@@ -165,12 +187,12 @@ struct SortWorkspace {
 inline int radix_sort_pairs(SortWorkspace& ws, uint32_t n, int key_bits, cudaStream_t st, uint32_t** keys_sorted,
                             uint32_t** perm) {
     // one spare bit above the cell keys so that the special keys (out of grid, migrated away) stay on top
-    const int passes = (key_bits + 8) / 8;
+    const int passes = (key_bits + kRadixBits) / kRadixBits;
     uint32_t *kin = ws.keys_a, *kout = ws.keys_b, *vin = nullptr, *vout = ws.vals_a;
     uint32_t* vother = ws.vals_b;
     int launches = 0;
     for (int p = 0; p < passes; ++p) {
-        const int shift = 8 * p;
+        const int shift = kRadixBits * p;
         sort_hist<<<ws.ntiles, kSortThreads, 0, st>>>(kin, n, shift, ws.hist, ws.ntiles);
         sort_scan<<<kRadix, 256, 0, st>>>(ws.hist, ws.ntiles, ws.digit_total, ws.digit_base, ws.done_counter);
         sort_scatter<<<ws.ntiles, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, shift, ws.hist, ws.ntiles,

@@ -113,10 +113,9 @@ def test_repaired_state_after_an_out_of_grid_error_starts_from_clean_grids():
     sim.upload(*[bad[k] for k in FIELDS])
     with pytest.raises(nm.OutOfGridError):
         sim.advance(2, sync=True)
-    z = np.zeros_like(x)
-    sim.upload(x, v, np.tile(np.eye(3, dtype=np.float32), (len(x), 1, 1)), np.zeros((len(x), 3, 3), np.float32),
-               np.ones(len(x), np.float32))
     cpu = co.CpuSim(x, co.JELLY, 48, v=v)
+    init = cpu.particles()                        # (the reference's initial F is diag<3>(1) = diag(1, 1, 0), Q1)
+    sim.upload(*[init[k] for k in FIELDS])
     for step in range(3):
         sim.advance(1, sync=True), cpu.advance(1)
         ref = cpu.particles()
