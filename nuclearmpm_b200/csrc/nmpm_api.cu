@@ -64,21 +64,21 @@ struct nmpm_sim {
     int fuse = 0;            // 0 off, 1 on (not on the first step after an upload: that state may be replaced again), 2 always
     bool p2g_ahead = false;  // grid_alt holds the P2G of store[cur] (the coming step) over box[box_cur]
     int grid_sel = 0;        // which of the two buffers `grid` is (CUDA-graph key)
-    int fused_minb = NMPM_FUSED_MINB;
-    // active node tiles (nmpm_kernels.cuh: k_tiles3; 3D, single GPU): one flag bit per 4^3-node tile, raised for the
-    // NEXT step's stencils by whoever produces the positions (G2P, the key pass), consumed by grid_op and the clear (NMPM_TILES=0: node boxes as in 2D / slabs)
-    // Ring like the node boxes and indexed like them: tile_ring[b] belongs to the positions box[b] bounds.
-    // batch of independent 2D scenes stacked along x (nmpm_create_batch*): MaterialParams::scenes / scene_of / lame
+    int fused_minb = NMPM_FUSED_MINB;  // CTAs per SM the fused kernel is compiled for (env NMPM_FUSED_MINB: experiments)
+    // Batch of independent 2D scenes stacked along x (nmpm_create_batch*): MaterialParams::scenes / scene_of / lame
     int scenes = 1;
     unsigned short* d_scene_of = nullptr;
     float2* d_lame = nullptr;
     std::vector<float2> lame_host;
+    // Active node tiles (nmpm_kernels.cuh: k_tile_decide, k_mark_tiles, k_tiles3; 3D, single GPU): one flag bit per
+    // 4^3-node tile, raised from the cell keys of the coming step, consumed by grid_op and the clear.  A ring like the
+    // node boxes and indexed like them: tile_ring[b] / d_tile_want[b] belong to the positions box[b] bounds.  The mode is
+    // decided on the device per step: d_tile_want[b] says whether the flags of slot b were raised; every tile / box kernel
+    // checks it and returns at once if it is not its turn.
     uint32_t* tile_ring[kBoxRing] = {nullptr, nullptr, nullptr, nullptr};
-    bool tiles = false;      // flag arrays allocated (3D, single GPU)
-    // Tile mode is adaptive and decided on the device per step (k_tile_decide): d_tile_want[b] says whether the flags of ring
-    // slot b were raised for the positions box[b] bounds; every tile / box kernel checks it and returns if it is not its turn.
-    int tile_policy = 0;     // nmpm_options.tiles: 0 adaptive, 1 never, 2 always
-    int* d_tile_want = nullptr;  // kBoxRing ints  // CTAs per SM the fused kernel is compiled for (env NMPM_FUSED_MINB: experiments)
+    int* d_tile_want = nullptr;  // kBoxRing ints
+    bool tiles = false;          // the arrays above exist (policy is not "never")
+    int tile_policy = 0;         // 0 adaptive (k_tile_decide), 1 never, 2 always — nmpm_options.tiles after the grid-size rule
     // node boxes (GridBox, device): box[box_cur] bounds the particles of the current step, box[(box_cur+3)%4]
     // the nodes the previous P2G wrote (cleared at the start of the next one), box[(box_cur+1)%4] is being
     // built by the G2P in flight
