@@ -38,10 +38,16 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist(const uint32_t* __rest
     const uint32_t start = blockIdx.x * kSortTile;
     // (plain shared-memory atomics: aggregating the lanes of equal digit with __match_any_sync first — cell-sorted keys
     // repeat their digit ~8 times in a row — was measured slower, 0.184 against 0.178 ms of sort per step, gpurun r3r)
+    uint32_t k[kSortItems];  // all loads in flight before the first atomic (the atomics order the loads behind them)
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
         const uint32_t idx = start + i * kSortThreads + threadIdx.x;
-        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & kRadixMask], 1u);
+        k[i] = (idx < n) ? __ldg(keys + idx) : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+        const uint32_t idx = start + i * kSortThreads + threadIdx.x;
+        if (idx < n) atomicAdd(&h[(k[i] >> shift) & kRadixMask], 1u);
     }
     __syncthreads();
     for (int d = threadIdx.x; d < kRadix; d += kSortThreads) hist[(size_t) d * ntiles + blockIdx.x] = h[d];
@@ -138,11 +144,16 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __r
     uint16_t rank[kSortItems];
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {  // all loads in flight before the ranking (its __syncwarp()s order them)
+        const uint32_t idx = wstart + i * 32 + lane;
+        const bool valid = idx < n;
+        key[i] = valid ? __ldg(keys_in + idx) : 0xFFFFFFFFu;
+        val[i] = valid ? (vals_in ? __ldg(vals_in + idx) : idx) : 0u;
+    }
+#pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
         const uint32_t idx = wstart + i * 32 + lane;
         const bool valid = idx < n;
-        key[i] = valid ? keys_in[idx] : 0xFFFFFFFFu;
-        val[i] = valid ? (vals_in ? vals_in[idx] : idx) : 0u;
         const uint32_t digit = (key[i] >> shift) & kRadixMask;
         // invalid lanes get a private pseudo-digit so that they match nobody
         const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : ((uint32_t) kRadix | (uint32_t) lane));
