@@ -1,5 +1,6 @@
 #!/bin/bash
-# GPU visit: bash tools/gpu_visit.sh <tag> [steps...]   steps: test fullres bench ref snow128 launches ncu cfg5
+# GPU visit: bash tools/gpu_visit.sh <tag> [steps...]   steps: test fullres fusedtest tiletest batchtest smoke bench quick
+#   quickoff (unfused) notiles alwaystiles minb6 abminb ref snow128|cfg1|cfg2|cfg3 launches ncu ncufused ncug2p occupancy cfg5
 tag=${1:-visit}; shift
 what=${@:-test bench}
 out=gpurun_out/$tag
@@ -14,11 +15,9 @@ quickoff) timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --fuse 1 > 
 abminb)  for mb in 5 8; do NMPM_FUSED_MINB=$mb timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --late-step 0 > $out/bench_minb$mb.json 2> $out/bench_minb$mb.err; echo "minb $mb rc=$?"; python tools/bench_summary.py $out/bench_minb$mb.json; done;;
 ncufused) timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_g2p_p2g' -s 28 -c 4 \
             -f -o $out/prof_cfg4_fused python tools/profile_step.py --workload cfg4 --warmup 28 --steps 6 --sort-every 4 > $out/ncu_fused.log 2>&1; echo "ncu rc=$?"; tail -2 $out/ncu_fused.log;;
-abflags) for cfg in "0 6 4" "2 6 4" "4 6 4" "6 6 4" "6 8 4" "6 6 2" "6 6 3" "6 8 2"; do set -- $cfg; NMPM_FUSED_FLAGS=$1 NMPM_FUSED_MINB=$2 timeout 600 python bench.py --steps 24 --warmup 5 --no-cpu --late-step 0 --sort-every $3 > $out/bench_f$1_b$2_s$3.json 2> $out/bench_f$1_b$2_s$3.err; echo "flags $1 minb $2 sort $3 rc=$?"; python tools/bench_summary.py $out/bench_f$1_b$2_s$3.json; done;;
 occupancy) timeout 900 python tools/grid_occupancy.py --workload cfg4 --steps 40 150 300 > $out/grid_occupancy.jsonl 2> $out/grid_occupancy.err; echo "occupancy rc=$?"; cat $out/grid_occupancy.jsonl;;
 notiles) NMPM_TILES=0 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu > $out/bench_quick_notiles.json 2> $out/bench_quick_notiles.err; echo "bench notiles rc=$?"; python tools/bench_summary.py $out/bench_quick_notiles.json;;
 minb6)   NMPM_FUSED_MINB=6 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu > $out/bench_quick_minb6.json 2> $out/bench_quick_minb6.err; echo "bench minb6 rc=$?"; python tools/bench_summary.py $out/bench_quick_minb6.json;;
-abtile)  for cfg in "0 1" "0 0" "1 0" "2 0" "3 0"; do set -- $cfg; NMPM_TILE_MODE=$1 NMPM_TILES_CONSUME=$2 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --late-step 0 --fuse 1 > $out/bench_tm$1_c$2.json 2> $out/bench_tm$1_c$2.err; echo "tile mode $1 consume $2 rc=$?"; python tools/bench_summary.py $out/bench_tm$1_c$2.json; done;;
 ncug2p)  NMPM_FUSE=0 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_g2p_gather' -s 30 -c 2 \
             -f -o $out/prof_cfg4_g2p python tools/profile_step.py --workload cfg4 --warmup 28 --steps 6 --sort-every 4 > $out/ncu_g2p.log 2>&1; echo "ncu rc=$?"; tail -2 $out/ncu_g2p.log;;
 batchtest) timeout 600 python -m pytest tests/test_batch_gpu.py -m gpu -q -x > $out/pytest_batch.log 2>&1; echo "batch pytest rc=$?"; tail -25 $out/pytest_batch.log;;
