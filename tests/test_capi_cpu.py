@@ -71,6 +71,25 @@ def test_invalid_arguments_rejected(lib):
     assert lib.nmpm_create_aos(2, 0, 64, 1e-4, 1e4, 0.2, -100.0, 4, x.ctypes.data, 8, None, ctypes.byref(h)) == 1
     assert lib.nmpm_advance(None, 1) == 1
     assert lib.nmpm_num_particles(None) == 0
+    # batches (nmpm_create_batch): nscenes >= 1, counts / E / nu required
+    counts = (ctypes.c_size_t * 2)(2, 2)
+    E = np.array([1e3, 2e3], np.float32).ctypes.data_as(fp)
+    assert lib.nmpm_create_batch(1, 64, 1e-4, -100.0, 0, counts, E, E, *args, None, ctypes.byref(h)) == 1
+    assert lib.nmpm_create_batch(1, 64, 1e-4, -100.0, 2, None, E, E, *args, None, ctypes.byref(h)) == 1
+    assert b"batch" in lib.nmpm_last_error(None)
+    assert lib.nmpm_num_scenes(None) == 0 and lib.nmpm_fused(None) == 0 and lib.nmpm_tiles_active(None) == 0
+
+
+def test_batch_has_no_cpu_fallback_either(lib):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present; the negative path is checked on the CPU box")
+    with pytest.raises(nm.NmpmError, match="no CUDA device"):
+        nm.MPMBatch([nm.cube(2, 5, 0.4, 0.6), nm.cube(2, 5, 0.2, 0.4)], nm.MaterialModel.kJelly, E=[1e3, 2e3], nu=[0.3, 0.3])
 
 
 def test_python_cube_matches_oracle_bitwise():
