@@ -22,7 +22,7 @@
 #include "nmpm_p2g_cell.cuh"
 
 #ifndef NMPM_FUSED_MINB
-#define NMPM_FUSED_MINB 8
+#define NMPM_FUSED_MINB 7
 #endif
 
 namespace nmpm {
@@ -249,7 +249,9 @@ inline void launch_g2p_p2g(const ParticleStore& S, const ParticleStore& T, const
 #define NMPM_FUSED_LAUNCH(B)                                                                                                \
     k_g2p_p2g<MODEL, B><<<blocks, 128, 0, st>>>(S, T, perm, n, P, grid, grid_next, keys_out, tiles_per_axis, error_flag, \
                                                 box_partial, local_reorder)
-    // CTAs per SM = register budget: 8 -> 64 registers, 6 -> 80, 5 -> 96 (NMPM_FUSED_MINB env: experiments)
+    // CTAs per SM = register budget: 8 -> 64 registers, 7 -> 72, 6 -> 80, 5 -> 96 (NMPM_FUSED_MINB env: experiments).
+    // Measured on cfg4 (fused launch): 5: 1.81 ms, 6: 1.76, 7: 1.725, 8: 1.76 — at 7 the 157 KB of packets leave the L1
+    // a 92 KB carve-out instead of 60 KB at 8 (gpurun r2r, r3v)
     if (minb >= 8) NMPM_FUSED_LAUNCH(8);
     else if (minb == 7) NMPM_FUSED_LAUNCH(7);
     else if (minb == 5) NMPM_FUSED_LAUNCH(5);
