@@ -416,6 +416,7 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
     // sort workspace
     const size_t nn = h->cap ? h->cap : 1;
     h->sort.ntiles = (uint32_t) ((nn + kSortTile - 1) / kSortTile);
+    if (const char* sm = std::getenv("NMPM_SORT_MINB")) h->sort.scatter_minb = std::atoi(sm);
     CUDA_TRY(h, cudaMalloc(&h->sort.keys_a, nn * sizeof(uint32_t)));
     CUDA_TRY(h, cudaMalloc(&h->sort.keys_b, nn * sizeof(uint32_t)));
     CUDA_TRY(h, cudaMalloc(&h->sort.vals_a, nn * sizeof(uint32_t)));

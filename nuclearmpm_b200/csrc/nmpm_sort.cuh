@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(256) sort_scan(uint32_t* __restrict__ hist, ui
 }
 
 // vals_in == nullptr means the identity (first pass).
-__global__ void __launch_bounds__(kSortThreads) sort_scatter(const uint32_t* __restrict__ keys_in,
+template <int MINB>
+__global__ void __launch_bounds__(kSortThreads, MINB) sort_scatter(const uint32_t* __restrict__ keys_in,
                                                              const uint32_t* __restrict__ vals_in,
                                                              uint32_t* __restrict__ keys_out,
                                                              uint32_t* __restrict__ vals_out, uint32_t n, int shift,
@@ -191,6 +192,9 @@ struct SortWorkspace {
     uint32_t *hist = nullptr, *digit_total = nullptr, *digit_base = nullptr;
     unsigned int* done_counter = nullptr;
     uint32_t ntiles = 0;
+    // CTAs per SM sort_scatter is compiled for (env NMPM_SORT_MINB: experiments).  3 (80 registers, 40 B of spills):
+    // 0.163 ms of sort per step on cfg4 against 0.170 without a bound (97 registers) and 0.214 at 2 (gpurun r3t, r3w)
+    int scatter_minb = 3;
 };
 
 // Sorts ws.keys_a (n keys) carrying slot indices; returns pointers to the sorted keys / permutation
@@ -206,8 +210,10 @@ inline int radix_sort_pairs(SortWorkspace& ws, uint32_t n, int key_bits, cudaStr
         const int shift = kRadixBits * p;
         sort_hist<<<ws.ntiles, kSortThreads, 0, st>>>(kin, n, shift, ws.hist, ws.ntiles);
         sort_scan<<<kRadix, 256, 0, st>>>(ws.hist, ws.ntiles, ws.digit_total, ws.digit_base, ws.done_counter);
-        sort_scatter<<<ws.ntiles, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, shift, ws.hist, ws.ntiles,
-                                                         ws.digit_base);
+        if (ws.scatter_minb >= 3)
+            sort_scatter<3><<<ws.ntiles, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, shift, ws.hist, ws.ntiles, ws.digit_base);
+        else
+            sort_scatter<2><<<ws.ntiles, kSortThreads, 0, st>>>(kin, vin, kout, vout, n, shift, ws.hist, ws.ntiles, ws.digit_base);
         launches += 3;
         uint32_t* t = kin;
         kin = kout;
