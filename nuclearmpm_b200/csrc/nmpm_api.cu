@@ -78,6 +78,7 @@ struct nmpm_sim {
     uint32_t* tile_ring[kBoxRing] = {nullptr, nullptr, nullptr, nullptr};
     int* d_tile_want = nullptr;  // kBoxRing ints
     bool tiles = false;          // the arrays above exist (policy is not "never")
+    int tiles_u = 4;             // flagged tiles in flight per warp of k_tiles3 (env NMPM_TILES_U: experiments)
     int tile_policy = 0;         // 0 adaptive (k_tile_decide), 1 never, 2 always — nmpm_options.tiles after the grid-size rule
     // node boxes (GridBox, device): box[box_cur] bounds the particles of the current step, box[(box_cur+3)%4]
     // the nodes the previous P2G wrote (cleared at the start of the next one), box[(box_cur+1)%4] is being
@@ -402,6 +403,7 @@ static int create_common(int dim, int model, int res, float dt, float E, float n
                 CUDA_TRY(h, cudaMemset(h->tile_ring[k], 0, bytes));
             }
             h->tiles = true;
+            if (const char* tu = std::getenv("NMPM_TILES_U")) h->tiles_u = std::atoi(tu);
             CUDA_TRY(h, cudaMalloc(&h->d_tile_want, kBoxRing * sizeof(int)));
             CUDA_TRY(h, cudaMemset(h->d_tile_want, 0, kBoxRing * sizeof(int)));
         }
@@ -798,7 +800,9 @@ static int ensure_box(nmpm_sim* h) {
 static void clear_grid(nmpm_sim* h, float4* grid, int box) {
     const int* want = h->tiles ? h->d_tile_want + box : nullptr;
     if (want) {
-        k_tiles3<0><<<kBoxBlocks, 256, 0, h->stream>>>(grid, h->tile_ring[box], h->P, want);
+        if (h->tiles_u == 8) k_tiles3<0, 8><<<kBoxBlocks, 256, 0, h->stream>>>(grid, h->tile_ring[box], h->P, want);
+        else if (h->tiles_u == 2) k_tiles3<0, 2><<<kBoxBlocks, 256, 0, h->stream>>>(grid, h->tile_ring[box], h->P, want);
+        else k_tiles3<0, 4><<<kBoxBlocks, 256, 0, h->stream>>>(grid, h->tile_ring[box], h->P, want);
         h->launches++;
     }
     NMPM_DISPATCH_DIM(h, (k_clear_box<D><<<kBoxBlocks, 256, 0, h->stream>>>(grid, h->d_box + box, h->P.n1,
@@ -886,7 +890,9 @@ static int do_p2g(nmpm_sim* h) {
 static int do_grid_op(nmpm_sim* h) {
     const int* want = h->tiles ? h->d_tile_want + h->box_cur : nullptr;
     if (want) {
-        k_tiles3<1><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->tile_ring[h->box_cur], h->P, want);
+        if (h->tiles_u == 8) k_tiles3<1, 8><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->tile_ring[h->box_cur], h->P, want);
+        else if (h->tiles_u == 2) k_tiles3<1, 2><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->tile_ring[h->box_cur], h->P, want);
+        else k_tiles3<1, 4><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->tile_ring[h->box_cur], h->P, want);
         h->launches++;
     }
     NMPM_DISPATCH_DIM(h, (k_grid_op<D><<<kBoxBlocks, 256, 0, h->stream>>>(h->grid, h->d_box + h->box_cur, h->P, want)));

